@@ -1,0 +1,1199 @@
+// api.cu -- host side of the C ABI declared in include/laboetie_gpu.h.
+//
+// One handle owns one GPU and one z-slab.  Device memory per node (fp64 SoA):
+//   f[2]   2 x 19   populations, two-lattice (source / destination of a step)
+//   mom    4        density, jx, jy, jz as the driver sees them
+//   jpp[2] 2 x 3    momentum density of the last two steps (for max|j - j_old|)
+//   mask   1 u32    fluid bit, 18 neighbour-is-fluid bits, interfacial bit
+// Phase B reuses f[0] for the 18 link probabilities and f[1] for the remaining
+// fraction / u*, both time levels of Propagated_Quantity and of the adsorbed
+// quantity (the reference drops its populations there too, drop_tracers.f90:85).
+//
+// Multi-GPU: the slab ring exchanges, per step, the 5 populations leaving each
+// z-face (ncclSend/ncclRecv straight from / into the contiguous boundary and halo
+// planes -- no packing), overlapped with the interior planes' kernel; scalars go
+// through ncclAllReduce.  NCCL is loaded with dlopen only when lbg_comm_init is
+// called, so single-GPU use has no NCCL dependency.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/laboetie_gpu.h"
+#include "lbg_internal.h"
+
+using namespace lbg;
+
+namespace {
+
+constexpr int SLOT_CAP = 4096;  // steps per batch (one host sync per batch)
+
+std::string g_last_error;
+
+struct Nccl {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) return false;
+#define LBG_SYM(f) *(void**)(&f) = dlsym(lib, "nccl" #f)
+    LBG_SYM(GetUniqueId);
+    LBG_SYM(CommInitRank);
+    LBG_SYM(CommDestroy);
+    LBG_SYM(GroupStart);
+    LBG_SYM(GroupEnd);
+    LBG_SYM(Send);
+    LBG_SYM(Recv);
+    LBG_SYM(AllReduce);
+    LBG_SYM(GetErrorString);
+#undef LBG_SYM
+    return GetUniqueId && CommInitRank && CommDestroy && GroupStart && GroupEnd && Send && Recv && AllReduce;
+  }
+} g_nccl;
+
+struct Force {
+  int mode = FORCE_NONE;  // FORCE_NONE / FORCE_UNIFORM / FORCE_FIELD
+  double u[3] = {0, 0, 0};
+  double* field = nullptr;  // 3 arrays, stride nalloc (owned)
+};
+
+enum Phase { PH_CREATED = 0, PH_LB = 1, PH_MP = 2 };
+
+}  // namespace
+
+struct lbg_handle_s {
+  int device = 0;
+  int sm_count = 148;
+  Geo geo{};
+  int lz_global = 0, k0 = 0;
+  long long nown = 0;
+  std::string err;
+  long long launches = 0;
+
+  int nranks = 1, rank = 0;
+  ncclComm_t comm = nullptr;
+  cudaStream_t st = nullptr, st_comm = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  bool halo_pending = false;
+
+  uint32_t* mask = nullptr;
+  double* f[2] = {nullptr, nullptr};
+  double* mom = nullptr;
+  double* jpp[2] = {nullptr, nullptr};
+  unsigned long long* l2_slots = nullptr;
+  double* vacf_slots = nullptr;
+  double* partial = nullptr;
+  Ctrl* ctrl = nullptr;
+  int* mp_err = nullptr;
+  unsigned long long* counts = nullptr;
+  // pinned host staging
+  unsigned long long* h_l2 = nullptr;
+  double* h_vacf = nullptr;
+  Ctrl* h_ctrl = nullptr;
+
+  d3q19::Consts k{};
+  int grid_lb = 148, grid_mp = 148;
+  int64_t n_fluid = 0, n_if_fluid = 0;  // own planes
+
+  Phase phase = PH_CREATED;
+  // Phase A
+  long long t = 0;
+  bool precollision = true;  // f[src] holds n(t) (not yet collided) since init/upload
+  int src = 0;               // f[src] = n*(t) (or n(t) if precollision); f[1-src] = n*(t+1) when collided_ok
+  int jc = 0;                // jpp[jc] = j(t) when j_valid_step == t
+  bool collided_ok = false;
+  double collided_tau = 0;
+  unsigned long long force_version = 0, collided_force_version = 0;
+  long long j_valid_step = -1, mom_valid_step = 0;
+  Force fcur, fprev;
+  bool prev_equals_cur = true;
+  // Phase B
+  long long it = 0;
+  int pc = 0;  // P[pc] = now
+  double Db = 0, ka = 0, kd = 0;
+  int ads = 0;
+  int mp_bad = 0;
+  double* q = nullptr;
+  double* s = nullptr;
+  double* P[2] = {nullptr, nullptr};
+  double* A[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+int fail(lbg_handle h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_last_error = msg;
+  return code;
+}
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return fail(h, e_ == cudaErrorMemoryAllocation ? LBG_ERR_NOMEM : LBG_ERR_CUDA,                \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                               \
+  } while (0)
+
+#define NK(call)                                                                                     \
+  do {                                                                                               \
+    ncclResult_t r_ = (call);                                                                        \
+    if (r_ != ncclSuccess)                                                                           \
+      return fail(h, LBG_ERR_NCCL,                                                                   \
+                  std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error")); \
+  } while (0)
+
+#define RET(call)               \
+  do {                          \
+    int rc_ = (call);           \
+    if (rc_ != LBG_OK) return rc_; \
+  } while (0)
+
+// module_lbmodel.f90:122-136, every operation rounded to fp64 like the Fortran PARAMETERs
+d3q19::Consts make_consts() {
+  d3q19::Consts k;
+  volatile double one = 1.0, three = 3.0, e18 = 18.0, e36 = 36.0;
+  const double csq = one / three;
+  const double w[3] = {one / three, one / e18, one / e36};
+  volatile double csq2 = csq * csq;
+  for (int i = 0; i < 3; ++i) {
+    k.a0[i] = w[i];
+    k.a1[i] = w[i] / csq;
+    k.a2[i] = w[i] / (2 * csq2);
+    k.two_a2[i] = 2.0 * k.a2[i];
+  }
+  k.csq = csq;
+  volatile double c1 = one - csq;
+  k.c1 = c1;
+  k.mcsq = 0.0 - csq;
+  return k;
+}
+
+long long own_begin(const lbg_handle h) { return h->geo.plane; }
+long long own_end(const lbg_handle h) { return (long long)h->geo.plane * (h->geo.nzl + 1); }
+
+int up_rank(const lbg_handle h) { return (h->rank + 1) % h->nranks; }
+int down_rank(const lbg_handle h) { return (h->rank + h->nranks - 1) % h->nranks; }
+
+// Exchange `narr` arrays' boundary planes with the ring neighbours.  up_list /
+// down_list name the arrays (index into base, stride nalloc) whose top own plane
+// goes to the upper neighbour's lower halo / whose bottom own plane goes to the
+// lower neighbour's upper halo.  Runs on st_comm after everything enqueued on st.
+int halo_exchange(lbg_handle h, double* base, const int* up_list, int nup, const int* down_list, int ndown) {
+  if (h->nranks == 1) return LBG_OK;
+  const Geo& g = h->geo;
+  const size_t cnt = (size_t)g.plane;
+  CK(cudaEventRecord(h->ev_ready, h->st));
+  CK(cudaStreamWaitEvent(h->st_comm, h->ev_ready, 0));
+  NK(g_nccl.GroupStart());
+  for (int i = 0; i < nup; ++i) {
+    double* a = base + (long long)up_list[i] * g.nalloc;
+    NK(g_nccl.Send(a + (long long)g.plane * g.nzl, cnt, ncclDouble, up_rank(h), h->comm, h->st_comm));
+    NK(g_nccl.Recv(a, cnt, ncclDouble, down_rank(h), h->comm, h->st_comm));
+  }
+  for (int i = 0; i < ndown; ++i) {
+    double* a = base + (long long)down_list[i] * g.nalloc;
+    NK(g_nccl.Send(a + (long long)g.plane, cnt, ncclDouble, down_rank(h), h->comm, h->st_comm));
+    NK(g_nccl.Recv(a + (long long)g.plane * (g.nzl + 1), cnt, ncclDouble, up_rank(h), h->comm, h->st_comm));
+  }
+  NK(g_nccl.GroupEnd());
+  CK(cudaEventRecord(h->ev_halo, h->st_comm));
+  h->halo_pending = true;
+  return LBG_OK;
+}
+
+int wait_halo(lbg_handle h) {
+  if (h->halo_pending) {
+    CK(cudaStreamWaitEvent(h->st, h->ev_halo, 0));
+    h->halo_pending = false;
+  }
+  return LBG_OK;
+}
+
+const int UP_L[5] = {5, 11, 12, 15, 16};     // cz = +1  (reference l = 6,12,13,16,17)
+const int DOWN_L[5] = {6, 13, 14, 17, 18};   // cz = -1  (reference l = 7,14,15,18,19)
+
+// all-reduce `n` doubles in place across the ring, ordered after st, result visible to st
+int allreduce(lbg_handle h, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t op) {
+  if (h->nranks == 1) return LBG_OK;
+  CK(cudaEventRecord(h->ev_ready, h->st));
+  CK(cudaStreamWaitEvent(h->st_comm, h->ev_ready, 0));
+  NK(g_nccl.AllReduce(buf, buf, n, dt, op, h->comm, h->st_comm));
+  CK(cudaEventRecord(h->ev_halo, h->st_comm));
+  h->halo_pending = true;
+  return LBG_OK;
+}
+
+int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nzl, const int8_t* nature_halo,
+                  int device, bool zwrap) {
+  lbg_handle h = nullptr;
+  if (!out || !nature_halo || lx < 1 || ly < 1 || lz_global < 1 || nzl < 1 || k0 < 0 || k0 + nzl > lz_global)
+    return fail(nullptr, LBG_ERR_INVALID_ARG, "lbg_create: invalid argument");
+  const long long plane = (long long)lx * ly;
+  const long long nalloc = plane * (nzl + 2);
+  if (nalloc > (long long)INT_MAX - 8) return fail(nullptr, LBG_ERR_INVALID_ARG, "lbg_create: slab too large for 32-bit node index");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(nullptr, LBG_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
+  if (device < 0 || device >= ndev) return fail(nullptr, LBG_ERR_INVALID_ARG, "lbg_create: bad device index");
+  h = new lbg_handle_s();
+  h->device = device;
+  h->geo.lx = lx;
+  h->geo.ly = ly;
+  h->geo.plane = (int)plane;
+  h->geo.nzl = nzl;
+  h->geo.zwrap = zwrap ? 1 : 0;
+  h->geo.nalloc = nalloc;
+  h->lz_global = lz_global;
+  h->k0 = k0;
+  h->nown = plane * nzl;
+  h->k = make_consts();
+  auto bail = [&](int rc) {
+    std::string e = h->err;
+    lbg_destroy(h);
+    g_last_error = e;
+    return rc;
+  };
+#define CKB(call)                                                                            \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+      return bail(e_ == cudaErrorMemoryAllocation ? LBG_ERR_NOMEM : LBG_ERR_CUDA);           \
+    }                                                                                        \
+  } while (0)
+  CKB(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CKB(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  CKB(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  CKB(cudaStreamCreateWithFlags(&h->st_comm, cudaStreamNonBlocking));
+  CKB(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+  CKB(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+  CKB(cudaEventCreate(&h->ev_t0));
+  CKB(cudaEventCreate(&h->ev_t1));
+  h->grid_lb = occupancy_grid_lb(h->sm_count);
+  h->grid_mp = occupancy_grid_mp(h->sm_count);
+  const size_t nb = (size_t)nalloc * sizeof(double);
+  CKB(cudaMalloc(&h->mask, (size_t)nalloc * sizeof(uint32_t)));
+  CKB(cudaMalloc(&h->f[0], 19 * nb));
+  CKB(cudaMalloc(&h->f[1], 19 * nb));
+  CKB(cudaMalloc(&h->mom, 4 * nb));
+  CKB(cudaMalloc(&h->jpp[0], 3 * nb));
+  CKB(cudaMalloc(&h->jpp[1], 3 * nb));
+  CKB(cudaMalloc(&h->l2_slots, SLOT_CAP * sizeof(unsigned long long)));
+  CKB(cudaMalloc(&h->vacf_slots, 3 * SLOT_CAP * sizeof(double)));
+  const int maxgrid = (h->grid_lb > h->grid_mp ? h->grid_lb : h->grid_mp) + 8;
+  CKB(cudaMalloc(&h->partial, 3 * (size_t)maxgrid * sizeof(double)));
+  CKB(cudaMalloc(&h->ctrl, sizeof(Ctrl)));
+  CKB(cudaMalloc(&h->mp_err, sizeof(int)));
+  CKB(cudaMalloc(&h->counts, 2 * sizeof(unsigned long long)));
+  CKB(cudaMallocHost(&h->h_l2, SLOT_CAP * sizeof(unsigned long long)));
+  CKB(cudaMallocHost(&h->h_vacf, 3 * SLOT_CAP * sizeof(double)));
+  CKB(cudaMallocHost(&h->h_ctrl, sizeof(Ctrl)));
+  CKB(cudaMemsetAsync(h->mask, 0, (size_t)nalloc * sizeof(uint32_t), h->st));
+  CKB(cudaMemsetAsync(h->f[0], 0, 19 * nb, h->st));
+  CKB(cudaMemsetAsync(h->f[1], 0, 19 * nb, h->st));
+  CKB(cudaMemsetAsync(h->mom, 0, 4 * nb, h->st));
+  CKB(cudaMemsetAsync(h->jpp[0], 0, 3 * nb, h->st));
+  CKB(cudaMemsetAsync(h->jpp[1], 0, 3 * nb, h->st));
+  CKB(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
+  CKB(cudaMemsetAsync(h->counts, 0, 2 * sizeof(unsigned long long), h->st));
+  // nature (with halo planes) is staged in f[1] and dropped once the masks exist
+  int8_t* nat_d = reinterpret_cast<int8_t*>(h->f[1]);
+  CKB(cudaMemcpyAsync(nat_d, nature_halo, (size_t)nalloc, cudaMemcpyHostToDevice, h->st));
+  h->launches += launch_build_mask(h->geo, nat_d, h->mask, h->st);
+  h->launches += launch_count_flags(h->geo, h->mask, h->counts, h->st);
+  CKB(cudaMemsetAsync(h->f[1], 0, (size_t)nalloc, h->st));
+  unsigned long long cnt[2];
+  CKB(cudaMemcpyAsync(cnt, h->counts, sizeof(cnt), cudaMemcpyDeviceToHost, h->st));
+  CKB(cudaStreamSynchronize(h->st));
+  CKB(cudaGetLastError());
+  h->n_fluid = (int64_t)cnt[0];
+  h->n_if_fluid = (int64_t)cnt[1];
+#undef CKB
+  *out = h;
+  return LBG_OK;
+}
+
+// which force was in effect for the last completed step (enters j(t) as f/2)
+const Force& force_of_last_step(const lbg_handle h) { return h->prev_equals_cur ? h->fcur : h->fprev; }
+
+int ensure_field(lbg_handle h, Force& f) {
+  if (!f.field) CK(cudaMalloc(&f.field, 3 * (size_t)h->geo.nalloc * sizeof(double)));
+  return LBG_OK;
+}
+
+// make `f` usable as a field (materialise a uniform force on fluid nodes)
+int as_field(lbg_handle h, Force& f, double** scratch, const double** out) {
+  if (f.mode == FORCE_FIELD) {
+    *out = f.field;
+    return LBG_OK;
+  }
+  if (!*scratch) CK(cudaMalloc(scratch, 3 * (size_t)h->geo.nalloc * sizeof(double)));
+  h->launches += launch_fill_force(h->geo, h->mask, f.u, *scratch, h->st);
+  *out = *scratch;
+  return LBG_OK;
+}
+
+struct ForceSel {
+  int mode;
+  double fj[3], fc[3];
+  const double *fj_field, *fc_field;
+};
+
+int select_force(lbg_handle h, Force& fj, Force& fc, ForceSel* s, double** scratch_j, double** scratch_c) {
+  std::memset(s, 0, sizeof(*s));
+  if (fj.mode != FORCE_FIELD && fc.mode != FORCE_FIELD) {
+    s->mode = (fj.mode == FORCE_NONE && fc.mode == FORCE_NONE) ? FORCE_NONE : FORCE_UNIFORM;
+    for (int d = 0; d < 3; ++d) {
+      s->fj[d] = fj.mode == FORCE_NONE ? 0.0 : fj.u[d];
+      s->fc[d] = fc.mode == FORCE_NONE ? 0.0 : fc.u[d];
+    }
+    return LBG_OK;
+  }
+  s->mode = FORCE_FIELD;
+  RET(as_field(h, fj, scratch_j, &s->fj_field));
+  if (&fj == &fc) s->fc_field = s->fj_field;
+  else RET(as_field(h, fc, scratch_c, &s->fc_field));
+  return LBG_OK;
+}
+
+struct StepFlags {
+  bool check, writej, redo;
+  int batch_idx, prev_checked, prev_may_stop;
+  double target;
+};
+
+// Enqueue kernel K: f[fin] -> f[1-fin] over own planes (+ halo exchange of the result).
+int enqueue_lb_kernel(lbg_handle h, int fin, double tau, const ForceSel& fs, int jold, const StepFlags& fl) {
+  LBArgs a{};
+  a.geo = h->geo;
+  a.k = h->k;
+  a.fin = h->f[fin];
+  a.fout = h->f[1 - fin];
+  a.mask = h->mask;
+  a.w1 = 1.0 - 1.0 / tau;
+  a.w2 = 1.0 / tau;
+  a.w3 = 1.0 - 1.0 / (2.0 * tau);
+  for (int d = 0; d < 3; ++d) {
+    a.fj[d] = fs.fj[d];
+    a.fc[d] = fs.fc[d];
+  }
+  a.fj_field = fs.fj_field;
+  a.fc_field = fs.fc_field;
+  a.jold = h->jpp[jold];
+  a.jnew = h->jpp[1 - jold];
+  a.l2_slots = h->l2_slots;
+  a.batch_idx = fl.batch_idx;
+  a.prev_checked = fl.prev_checked;
+  a.prev_may_stop = fl.prev_may_stop;
+  a.target = fl.target;
+  a.ctrl = h->ctrl;
+  const bool tau1 = (tau == 1.0);
+  const Geo& g = h->geo;
+  RET(wait_halo(h));
+  if (h->nranks == 1) {
+    a.g_begin = own_begin(h);
+    a.g_end = own_end(h);
+    h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->grid_lb, h->st);
+  } else {
+    // boundary planes first, so their populations can travel while the interior runs
+    a.g_begin = g.plane;
+    a.g_end = 2LL * g.plane;
+    h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->grid_lb, h->st);
+    if (g.nzl > 1) {
+      a.g_begin = (long long)g.plane * g.nzl;
+      a.g_end = (long long)g.plane * (g.nzl + 1);
+      h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->grid_lb, h->st);
+    }
+    RET(halo_exchange(h, h->f[1 - fin], UP_L, 5, DOWN_L, 5));
+    if (g.nzl > 2) {
+      a.g_begin = 2LL * g.plane;
+      a.g_end = (long long)g.plane * g.nzl;
+      h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->grid_lb, h->st);
+    }
+    if (fl.check) {
+      // global max of l2err, and the negative-population flag, before the next step looks at them
+      RET(wait_halo(h));
+      RET(allreduce(h, h->l2_slots + fl.batch_idx, 1, ncclUint64, ncclMax));
+      RET(wait_halo(h));
+      RET(allreduce(h, &h->ctrl->neg_step_idx, 1, ncclInt32, ncclMax));
+    }
+  }
+  return LBG_OK;
+}
+
+// Make f[1-src] = n*(t+1) valid for (tau, current force); optionally make j(t) available in jpp[jc].
+int ensure_collided(lbg_handle h, double tau, bool need_j) {
+  const bool stale = !h->collided_ok || tau != h->collided_tau || h->collided_force_version != h->force_version;
+  const bool j_missing = need_j && h->j_valid_step != h->t;
+  if (!stale && !j_missing) return LBG_OK;
+  double *scr_j = nullptr, *scr_c = nullptr;
+  int rc = LBG_OK;
+  if (h->precollision) {
+    ForceSel fs;
+    rc = select_force(h, h->fcur, h->fcur, &fs, &scr_c, &scr_c);
+    if (rc == LBG_OK) {
+      CollideArgs a{};
+      a.geo = h->geo;
+      a.k = h->k;
+      a.fin = h->f[h->src];
+      a.fout = h->f[1 - h->src];
+      a.mask = h->mask;
+      a.mom = h->mom;
+      a.g_begin = own_begin(h);
+      a.g_end = own_end(h);
+      a.w1 = 1.0 - 1.0 / tau;
+      a.w2 = 1.0 / tau;
+      a.w3 = 1.0 - 1.0 / (2.0 * tau);
+      for (int d = 0; d < 3; ++d) a.fc[d] = fs.fc[d];
+      a.fc_field = fs.fc_field;
+      rc = wait_halo(h);
+      if (rc == LBG_OK) {
+        h->launches += launch_collide(a, tau == 1.0, fs.mode, h->grid_lb, h->st);
+        rc = halo_exchange(h, h->f[1 - h->src], UP_L, 5, DOWN_L, 5);
+      }
+      if (rc == LBG_OK && j_missing) {
+        const size_t nb = (size_t)h->geo.nalloc * sizeof(double);
+        cudaError_t e = cudaMemcpyAsync(h->jpp[h->jc], h->mom + h->geo.nalloc, 3 * nb, cudaMemcpyDeviceToDevice, h->st);
+        if (e != cudaSuccess) rc = fail(h, LBG_ERR_CUDA, cudaGetErrorString(e));
+        h->j_valid_step = h->t;
+      }
+    }
+  } else {
+    // redo K(t): pull n*(t) from f[src], force of step t for j(t), current force for the collision
+    Force& fj = h->prev_equals_cur ? h->fcur : h->fprev;
+    ForceSel fs;
+    rc = select_force(h, fj, h->fcur, &fs, &scr_j, &scr_c);
+    if (rc == LBG_OK) {
+      StepFlags fl{};
+      fl.check = false;
+      fl.writej = j_missing;
+      fl.redo = true;
+      // K(t) writes j(t) into jpp[1-jold]; keep jc pointing at j(t)
+      rc = enqueue_lb_kernel(h, h->src, tau, fs, 1 - h->jc, fl);
+      if (rc == LBG_OK && j_missing) h->j_valid_step = h->t;
+    }
+  }
+  if (scr_j || scr_c) {
+    cudaStreamSynchronize(h->st);
+    cudaFree(scr_j);
+    cudaFree(scr_c);
+  }
+  if (rc != LBG_OK) return rc;
+  h->collided_ok = true;
+  h->collided_tau = tau;
+  h->collided_force_version = h->force_version;
+  return LBG_OK;
+}
+
+int refresh_moments(lbg_handle h, double* pops_out) {
+  if (h->phase != PH_LB) return fail(h, LBG_ERR_STATE, "no Lattice-Boltzmann state (call lbg_lb_init first)");
+  if (h->precollision) {
+    if (pops_out) return LBG_OK;  // caller copies f[src] directly
+    return LBG_OK;                // mom holds the state the driver set
+  }
+  if (h->mom_valid_step == h->t && !pops_out) return LBG_OK;
+  Force fj = force_of_last_step(h);
+  double* scr = nullptr;
+  MomArgs a{};
+  a.geo = h->geo;
+  a.fin = h->f[h->src];
+  a.mask = h->mask;
+  a.mom = h->mom;
+  a.pops = pops_out;
+  a.g_begin = own_begin(h);
+  a.g_end = own_end(h);
+  int mode = fj.mode;
+  for (int d = 0; d < 3; ++d) a.fj[d] = fj.mode == FORCE_NONE ? 0.0 : fj.u[d];
+  a.fj_field = fj.field;
+  RET(wait_halo(h));
+  h->launches += launch_moments(a, mode, h->grid_lb, h->st);
+  (void)scr;
+  h->mom_valid_step = h->t;
+  return LBG_OK;
+}
+
+int snapshot_prev_force(lbg_handle h) {
+  if (!h->prev_equals_cur) return LBG_OK;
+  h->fprev.mode = h->fcur.mode;
+  for (int d = 0; d < 3; ++d) h->fprev.u[d] = h->fcur.u[d];
+  if (h->fcur.mode == FORCE_FIELD) {
+    RET(ensure_field(h, h->fprev));
+    CK(cudaMemcpyAsync(h->fprev.field, h->fcur.field, 3 * (size_t)h->geo.nalloc * sizeof(double),
+                       cudaMemcpyDeviceToDevice, h->st));
+  }
+  h->prev_equals_cur = false;
+  return LBG_OK;
+}
+
+int copy_own_to_host(lbg_handle h, double* dst, const double* src_arr) {
+  CK(cudaMemcpyAsync(dst, src_arr + h->geo.plane, (size_t)h->nown * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  return LBG_OK;
+}
+
+int copy_own_to_device(lbg_handle h, double* dst_arr, const double* src) {
+  CK(cudaMemcpyAsync(dst_arr + h->geo.plane, src, (size_t)h->nown * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  return LBG_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+int lbg_abi_version(void) { return LBG_ABI_VERSION; }
+
+const char* lbg_status_string(int s) {
+  switch (s) {
+    case LBG_OK: return "ok";
+    case LBG_ERR_NEGATIVE_POPULATION: return "In equilibration, the population n(x,y,z,vel) < 0";
+    case LBG_ERR_RESTPART_NEGATIVE: return "somewhere restpart is negative";
+    case LBG_ERR_RELAXATION_TIME: return "relaxation_time must be > 0.5";
+    case LBG_ERR_TRACER_DB: return "The diffusion coefficient (tracer_Db in input file) is invalid";
+    case LBG_ERR_TRACER_KA_KD: return "I detected tracer%ka or tracer%kd to be <0 in module moment_propagation";
+    case LBG_ERR_ALL_SOLID: return "All nodes are solid: no fluid, no fluid dynamics!";
+    case LBG_ERR_INVALID_ARG: return "invalid argument";
+    case LBG_ERR_STATE: return "call order violated";
+    case LBG_ERR_UNSUPPORTED: return "unsupported option";
+    case LBG_ERR_NO_DEVICE: return "no CUDA device (there is no CPU path)";
+    case LBG_ERR_CUDA: return "CUDA error";
+    case LBG_ERR_NCCL: return "NCCL error";
+    case LBG_ERR_NOMEM: return "out of device memory";
+    default: return "unknown status";
+  }
+}
+
+const char* lbg_last_error(lbg_handle h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int lbg_device_count(int* count) {
+  if (!count) return LBG_ERR_INVALID_ARG;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
+  *count = n;
+  return LBG_OK;
+}
+
+int lbg_partition(int lz, int nranks, int rank, int* k0, int* nzl) {
+  if (lz < 1 || nranks < 1 || rank < 0 || rank >= nranks || nranks > lz || !k0 || !nzl) return LBG_ERR_INVALID_ARG;
+  const int base = lz / nranks, extra = lz % nranks;
+  *nzl = base + (rank < extra ? 1 : 0);
+  *k0 = rank * base + (rank < extra ? rank : extra);
+  return LBG_OK;
+}
+
+int lbg_halo_plan(int up[5], int down[5]) {
+  if (!up || !down) return LBG_ERR_INVALID_ARG;
+  for (int i = 0; i < 5; ++i) {
+    up[i] = UP_L[i];
+    down[i] = DOWN_L[i];
+  }
+  return LBG_OK;
+}
+
+int lbg_create(lbg_handle* out, int lx, int ly, int lz, const int8_t* nature, int device) {
+  if (!nature || lx < 1 || ly < 1 || lz < 1) return fail(nullptr, LBG_ERR_INVALID_ARG, "lbg_create: invalid argument");
+  const size_t plane = (size_t)lx * ly;
+  bool any_fluid = false;
+  for (size_t i = 0; i < plane * lz && !any_fluid; ++i) any_fluid = nature[i] == 0;
+  if (!any_fluid) return fail(nullptr, LBG_ERR_ALL_SOLID, lbg_status_string(LBG_ERR_ALL_SOLID));
+  std::vector<int8_t> nat(plane * ((size_t)lz + 2));
+  std::memcpy(nat.data() + plane, nature, plane * lz);
+  std::memcpy(nat.data(), nature + plane * (lz - 1), plane);               // plane k = -1  == lz-1
+  std::memcpy(nat.data() + plane * ((size_t)lz + 1), nature, plane);       // plane k = lz  == 0
+  return create_common(out, lx, ly, lz, 0, lz, nat.data(), device, true);
+}
+
+int lbg_create_slab(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nzl, const int8_t* nature_halo,
+                    int device) {
+  return create_common(out, lx, ly, lz_global, k0, nzl, nature_halo, device, false);
+}
+
+int lbg_destroy(lbg_handle h) {
+  if (!h) return LBG_OK;
+  cudaSetDevice(h->device);
+  if (h->st) cudaStreamSynchronize(h->st);
+  if (h->st_comm) cudaStreamSynchronize(h->st_comm);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  cudaFree(h->mask);
+  cudaFree(h->f[0]);
+  cudaFree(h->f[1]);
+  cudaFree(h->mom);
+  cudaFree(h->jpp[0]);
+  cudaFree(h->jpp[1]);
+  cudaFree(h->l2_slots);
+  cudaFree(h->vacf_slots);
+  cudaFree(h->partial);
+  cudaFree(h->ctrl);
+  cudaFree(h->mp_err);
+  cudaFree(h->counts);
+  cudaFree(h->fcur.field);
+  cudaFree(h->fprev.field);
+  cudaFreeHost(h->h_l2);
+  cudaFreeHost(h->h_vacf);
+  cudaFreeHost(h->h_ctrl);
+  if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+  if (h->ev_halo) cudaEventDestroy(h->ev_halo);
+  if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+  if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+  if (h->st) cudaStreamDestroy(h->st);
+  if (h->st_comm) cudaStreamDestroy(h->st_comm);
+  delete h;
+  return LBG_OK;
+}
+
+int lbg_comm_unique_id(void* id_out) {
+  lbg_handle h = nullptr;
+  if (!id_out) return LBG_ERR_INVALID_ARG;
+  if (!g_nccl.load()) return fail(nullptr, LBG_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : ""));
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == LBG_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  NK(g_nccl.GetUniqueId(&id));
+  std::memcpy(id_out, &id, sizeof(id));
+  return LBG_OK;
+}
+
+int lbg_comm_init(lbg_handle h, int nranks, int rank, const void* id) {
+  if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return LBG_ERR_INVALID_ARG;
+  if (nranks == 1) return LBG_OK;
+  if (h->geo.zwrap) return fail(h, LBG_ERR_STATE, "lbg_comm_init needs a handle made by lbg_create_slab");
+  if (!g_nccl.load()) return fail(h, LBG_ERR_NCCL, "cannot load libnccl.so.2");
+  CK(cudaSetDevice(h->device));
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  NK(g_nccl.CommInitRank(&h->comm, nranks, uid, rank));
+  h->nranks = nranks;
+  h->rank = rank;
+  return LBG_OK;
+}
+
+int lbg_get_interfacial(lbg_handle h, int8_t* out) {
+  if (!h || !out) return LBG_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  int8_t* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)h->nown));
+  h->launches += launch_extract_flag(h->geo, h->mask, MASK_INTERFACIAL, d, h->st);
+  CK(cudaMemcpyAsync(out, d, (size_t)h->nown, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  cudaFree(d);
+  return LBG_OK;
+}
+
+int lbg_get_counts(lbg_handle h, int64_t* nf, int64_t* nif) {
+  if (!h) return LBG_ERR_INVALID_ARG;
+  if (nf) *nf = h->n_fluid;
+  if (nif) *nif = h->n_if_fluid;
+  return LBG_OK;
+}
+
+// --------------------------------------------------------------------------- Phase A
+static void reset_lb_state(lbg_handle h) {
+  h->phase = PH_LB;
+  h->t = 0;
+  h->precollision = true;
+  h->src = 0;
+  h->jc = 0;
+  h->collided_ok = false;
+  h->j_valid_step = -1;
+  h->mom_valid_step = 0;
+  h->fcur.mode = FORCE_NONE;
+  h->fprev.mode = FORCE_NONE;
+  for (int d = 0; d < 3; ++d) h->fcur.u[d] = h->fprev.u[d] = 0.0;
+  h->prev_equals_cur = true;
+  h->force_version++;
+}
+
+int lbg_lb_init(lbg_handle h, double rho0) {
+  if (!h) return LBG_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  const size_t nb = (size_t)h->geo.nalloc * sizeof(double);
+  CK(cudaMemsetAsync(h->f[0], 0, 19 * nb, h->st));
+  CK(cudaMemsetAsync(h->f[1], 0, 19 * nb, h->st));
+  CK(cudaMemsetAsync(h->mom, 0, 4 * nb, h->st));
+  CK(cudaMemsetAsync(h->jpp[0], 0, 3 * nb, h->st));
+  CK(cudaMemsetAsync(h->jpp[1], 0, 3 * nb, h->st));
+  h->launches += launch_lb_init(h->geo, h->mask, rho0, h->k.a0, h->f[0], h->mom, h->st);
+  CK(cudaGetLastError());
+  reset_lb_state(h);
+  return LBG_OK;
+}
+
+int lbg_lb_upload(lbg_handle h, const double* n, const double* rho, const double* jx, const double* jy,
+                  const double* jz) {
+  if (!h || !n || !rho || !jx || !jy || !jz) return LBG_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  const size_t nb = (size_t)h->geo.nalloc * sizeof(double);
+  CK(cudaMemsetAsync(h->f[0], 0, 19 * nb, h->st));
+  CK(cudaMemsetAsync(h->f[1], 0, 19 * nb, h->st));
+  CK(cudaMemsetAsync(h->mom, 0, 4 * nb, h->st));
+  CK(cudaMemsetAsync(h->jpp[0], 0, 3 * nb, h->st));
+  CK(cudaMemsetAsync(h->jpp[1], 0, 3 * nb, h->st));
+  for (int l = 0; l < 19; ++l) RET(copy_own_to_device(h, h->f[0] + (long long)l * h->geo.nalloc, n + (size_t)l * h->nown));
+  const double* m[4] = {rho, jx, jy, jz};
+  for (int c = 0; c < 4; ++c) RET(copy_own_to_device(h, h->mom + (long long)c * h->geo.nalloc, m[c]));
+  CK(cudaStreamSynchronize(h->st));
+  reset_lb_state(h);
+  return LBG_OK;
+}
+
+int lbg_lb_set_force_uniform(lbg_handle h, const double f[3]) {
+  if (!h || !f) return LBG_ERR_INVALID_ARG;
+  if (h->phase != PH_LB) return fail(h, LBG_ERR_STATE, "lbg_lb_set_force_uniform before lbg_lb_init");
+  CK(cudaSetDevice(h->device));
+  RET(snapshot_prev_force(h));
+  const bool zero = (f[0] == 0.0 && f[1] == 0.0 && f[2] == 0.0);
+  h->fcur.mode = zero ? FORCE_NONE : FORCE_UNIFORM;
+  for (int d = 0; d < 3; ++d) h->fcur.u[d] = f[d];
+  h->force_version++;
+  return LBG_OK;
+}
+
+int lbg_lb_set_force_field(lbg_handle h, const double* fx, const double* fy, const double* fz) {
+  if (!h || !fx || !fy || !fz) return LBG_ERR_INVALID_ARG;
+  if (h->phase != PH_LB) return fail(h, LBG_ERR_STATE, "lbg_lb_set_force_field before lbg_lb_init");
+  CK(cudaSetDevice(h->device));
+  RET(snapshot_prev_force(h));
+  RET(ensure_field(h, h->fcur));
+  CK(cudaMemsetAsync(h->fcur.field, 0, 3 * (size_t)h->geo.nalloc * sizeof(double), h->st));
+  const double* src[3] = {fx, fy, fz};
+  for (int d = 0; d < 3; ++d) RET(copy_own_to_device(h, h->fcur.field + (long long)d * h->geo.nalloc, src[d]));
+  CK(cudaStreamSynchronize(h->st));
+  h->fcur.mode = FORCE_FIELD;
+  h->force_version++;
+  return LBG_OK;
+}
+
+int lbg_lb_time(lbg_handle h, int64_t* t) {
+  if (!h || !t) return LBG_ERR_INVALID_ARG;
+  *t = h->t;
+  return LBG_OK;
+}
+
+int lbg_lb_step(lbg_handle h, double tau, int nsteps, int check_every, double target_error, double* l2err_hist,
+                int* steps_done, int* converged) {
+  if (!h || nsteps < 0 || check_every < 0) return LBG_ERR_INVALID_ARG;
+  if (steps_done) *steps_done = 0;
+  if (converged) *converged = 0;
+  if (h->phase != PH_LB) return fail(h, LBG_ERR_STATE, "lbg_lb_step needs lbg_lb_init/lbg_lb_upload first");
+  if (!(tau > 0.0) || tau < 0.5) return fail(h, LBG_ERR_RELAXATION_TIME, lbg_status_string(LBG_ERR_RELAXATION_TIME));
+  CK(cudaSetDevice(h->device));
+  auto checked = [&](long long s) { return check_every > 0 && (s % check_every) == 0; };
+  int total = 0;
+  while (total < nsteps) {
+    const int chunk = (nsteps - total) < SLOT_CAP ? (nsteps - total) : SLOT_CAP;
+    CK(cudaMemsetAsync(h->l2_slots, 0, (size_t)chunk * sizeof(unsigned long long), h->st));
+    CK(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
+    RET(ensure_collided(h, tau, checked(h->t + 1)));
+    ForceSel fs;
+    double* scr = nullptr;
+    RET(select_force(h, h->fcur, h->fcur, &fs, &scr, &scr));
+    int fin = 1 - h->src, jold = h->jc;
+    for (int i = 0; i < chunk; ++i) {
+      const long long s = h->t + 1 + i;
+      StepFlags fl{};
+      fl.check = checked(s);
+      fl.writej = fl.check || checked(s + 1);
+      fl.batch_idx = i;
+      fl.prev_checked = (i > 0 && checked(s - 1)) ? 1 : 0;
+      fl.prev_may_stop = (s - 1 > 2) ? 1 : 0;
+      fl.target = target_error;
+      RET(enqueue_lb_kernel(h, fin, tau, fs, jold, fl));
+      fin = 1 - fin;
+      jold = 1 - jold;
+    }
+    RET(wait_halo(h));
+    CK(cudaMemcpyAsync(h->h_l2, h->l2_slots, (size_t)chunk * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaGetLastError());
+    if (scr) cudaFree(scr);
+    int executed = chunk, conv = 0, neg = 0;
+    if (h->h_ctrl->neg_step_idx) {
+      executed = h->h_ctrl->neg_step_idx;
+      neg = 1;
+    }
+    for (int i = 0; i < executed; ++i) {
+      const long long s = h->t + 1 + i;
+      double v = std::numeric_limits<double>::quiet_NaN();
+      if (checked(s)) std::memcpy(&v, &h->h_l2[i], sizeof(double));
+      if (l2err_hist) l2err_hist[total + i] = v;
+      if (neg && i == executed - 1) break;  // the reference stops before l2err on that step
+      if (checked(s) && s > 2 && v <= target_error) {  // equilibration.f90:346
+        executed = i + 1;
+        conv = 1;
+        break;
+      }
+    }
+    // bookkeeping: `executed` kernels ran to completion, later ones returned at once
+    h->t += executed;
+    if (executed > 0) {
+      h->precollision = false;
+      if (executed & 1) {
+        h->src = 1 - h->src;
+        h->jc = 1 - h->jc;
+      }
+      const long long last = h->t;
+      if (checked(last) || checked(last + 1)) h->j_valid_step = last;
+      h->prev_equals_cur = true;
+      h->collided_ok = true;
+      h->collided_tau = tau;
+      h->collided_force_version = h->force_version;
+    }
+    total += executed;
+    if (steps_done) *steps_done = total;
+    if (neg) return fail(h, LBG_ERR_NEGATIVE_POPULATION, lbg_status_string(LBG_ERR_NEGATIVE_POPULATION));
+    if (conv) {
+      if (converged) *converged = 1;
+      break;
+    }
+  }
+  return LBG_OK;
+}
+
+int lbg_lb_download_moments(lbg_handle h, double* rho, double* jx, double* jy, double* jz) {
+  if (!h) return LBG_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  RET(refresh_moments(h, nullptr));
+  double* dst[4] = {rho, jx, jy, jz};
+  for (int c = 0; c < 4; ++c)
+    if (dst[c]) RET(copy_own_to_host(h, dst[c], h->mom + (long long)c * h->geo.nalloc));
+  CK(cudaStreamSynchronize(h->st));
+  return LBG_OK;
+}
+
+int lbg_lb_download_populations(lbg_handle h, double* n) {
+  if (!h || !n) return LBG_ERR_INVALID_ARG;
+  if (h->phase != PH_LB) return fail(h, LBG_ERR_STATE, "no Lattice-Boltzmann state");
+  CK(cudaSetDevice(h->device));
+  const double* from;
+  if (h->precollision) {
+    from = h->f[h->src];
+  } else {
+    // n(t) is rebuilt by a pull from n*(t); the destination buffer is used as scratch
+    RET(refresh_moments(h, h->f[1 - h->src]));
+    h->collided_ok = false;
+    from = h->f[1 - h->src];
+  }
+  for (int l = 0; l < 19; ++l) RET(copy_own_to_host(h, n + (size_t)l * h->nown, from + (long long)l * h->geo.nalloc));
+  CK(cudaStreamSynchronize(h->st));
+  return LBG_OK;
+}
+
+int lbg_lb_profiles(lbg_handle h, int axis, int raw, double* out) {
+  if (!h || !out || axis < 0 || axis > 2) return LBG_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  RET(refresh_moments(h, nullptr));
+  const int rows = axis == 0 ? h->geo.lx : (axis == 1 ? h->geo.ly : h->geo.nzl);
+  double* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)rows * 5 * sizeof(double)));
+  ProfileArgs a{};
+  a.geo = h->geo;
+  a.mom = h->mom;
+  a.axis = axis;
+  a.eps = std::numeric_limits<double>::epsilon();
+  a.out = d;
+  h->launches += launch_profile(a, rows, h->st);
+  std::vector<double> tmp((size_t)rows * 5);
+  CK(cudaMemcpyAsync(tmp.data(), d, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  cudaFree(d);
+  for (int p = 0; p < rows; ++p) {
+    if (raw) {
+      for (int c = 0; c < 5; ++c) out[(size_t)p * 5 + c] = tmp[(size_t)p * 5 + c];
+    } else {
+      out[(size_t)p * 4 + 0] = tmp[(size_t)p * 5 + 0];
+      out[(size_t)p * 4 + 1] = tmp[(size_t)p * 5 + 1];
+      out[(size_t)p * 4 + 2] = tmp[(size_t)p * 5 + 2];
+      const double cnt = tmp[(size_t)p * 5 + 4];
+      out[(size_t)p * 4 + 3] = tmp[(size_t)p * 5 + 3] / (cnt > 1.0 ? cnt : 1.0);
+    }
+  }
+  return LBG_OK;
+}
+
+int lbg_lb_total_flux(lbg_handle h, double out[3]) {
+  if (!h || !out) return LBG_ERR_INVALID_ARG;
+  std::vector<double> prof((size_t)h->geo.nzl * 5);
+  RET(lbg_lb_profiles(h, 2, 1, prof.data()));
+  out[0] = out[1] = out[2] = 0.0;
+  for (int p = 0; p < h->geo.nzl; ++p)
+    for (int c = 0; c < 3; ++c) out[c] += prof[(size_t)p * 5 + c];
+  return LBG_OK;
+}
+
+int lbg_lb_probe(lbg_handle h, int i, int j, int k, double out[4]) {
+  if (!h || !out || i < 0 || j < 0 || k < 0 || i >= h->geo.lx || j >= h->geo.ly || k >= h->geo.nzl) return LBG_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  RET(refresh_moments(h, nullptr));
+  const long long g = (long long)i + (long long)h->geo.lx * j + (long long)h->geo.plane * (k + 1);
+  // out = jx, jy, jz, density
+  for (int c = 0; c < 4; ++c)
+    CK(cudaMemcpyAsync(&out[c], h->mom + (long long)((c + 1) % 4) * h->geo.nalloc + g, sizeof(double),
+                       cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return LBG_OK;
+}
+
+// --------------------------------------------------------------------------- Phase B
+int lbg_mp_init(lbg_handle h, double Db, double ka, double kd, const double f_ext[3], double vacf0[3]) {
+  if (!h || !f_ext) return LBG_ERR_INVALID_ARG;
+  if (h->phase != PH_LB) return fail(h, LBG_ERR_STATE, "lbg_mp_init needs the Lattice-Boltzmann state (density, momentum)");
+  const double eps = std::numeric_limits<double>::epsilon();
+  if (Db <= eps) return fail(h, LBG_ERR_TRACER_DB, lbg_status_string(LBG_ERR_TRACER_DB));       // drop_tracers.f90:89
+  if (ka < -eps || kd < -eps) return fail(h, LBG_ERR_TRACER_KA_KD, lbg_status_string(LBG_ERR_TRACER_KA_KD));
+  CK(cudaSetDevice(h->device));
+  RET(refresh_moments(h, nullptr));
+  const Geo& g = h->geo;
+  if (h->nranks > 1) {
+    const int all4[4] = {0, 1, 2, 3};
+    RET(halo_exchange(h, h->mom, all4, 4, all4, 4));
+    RET(wait_halo(h));
+  }
+  // module_moment_propagation.f90:46-56,68,97
+  const double K = (std::fabs(kd) <= eps) ? 0.0 : ka / kd;
+  h->ads = std::fabs(K) > eps ? 1 : 0;
+  h->Db = Db;
+  h->ka = ka;
+  h->kd = kd;
+  long long nf = h->n_fluid, nif = h->n_if_fluid;
+  if (h->nranks > 1) {
+    unsigned long long c2[2] = {(unsigned long long)nf, (unsigned long long)nif};
+    CK(cudaMemcpyAsync(h->counts, c2, sizeof(c2), cudaMemcpyHostToDevice, h->st));
+    RET(allreduce(h, h->counts, 2, ncclUint64, ncclSum));
+    RET(wait_halo(h));
+    CK(cudaMemcpyAsync(c2, h->counts, sizeof(c2), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    nf = (long long)c2[0];
+    nif = (long long)c2[1];
+  }
+  const double Pstat = (double)nf + K * (double)nif;
+  volatile double one = 1.0, three = 3.0;
+  const double kBT = one / three;
+  const double lambda = 4.0 * Db / kBT;
+  // Phase B aliases the population buffers
+  const size_t nb = (size_t)g.nalloc * sizeof(double);
+  h->q = h->f[0];
+  h->s = h->f[1];
+  h->P[0] = h->f[1] + 4 * g.nalloc;
+  h->P[1] = h->f[1] + 7 * g.nalloc;
+  h->A[0] = h->f[1] + 10 * g.nalloc;
+  h->A[1] = h->f[1] + 13 * g.nalloc;
+  CK(cudaMemsetAsync(h->f[1], 0, 19 * nb, h->st));
+  CK(cudaMemsetAsync(h->mp_err, 0, sizeof(int), h->st));
+  CK(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
+  MPInitArgs a{};
+  a.geo = g;
+  a.k = h->k;
+  a.mask = h->mask;
+  a.mom = h->mom;
+  a.q = h->q;
+  a.s = h->s;
+  a.P0 = h->P[0];
+  a.g_begin = own_begin(h);
+  a.g_end = own_end(h);
+  for (int d = 0; d < 3; ++d) a.f[d] = f_ext[d];
+  for (int i = 0; i < 3; ++i) a.lambda_w[i] = lambda * h->k.a0[i];
+  a.bw = 1.0 / Pstat;
+  a.ka = ka;
+  a.ads = h->ads;
+  a.partial = h->partial;
+  a.err = h->mp_err;
+  const long long nblk = (h->nown + BLOCK - 1) / BLOCK;
+  const int grid = (int)(nblk < h->grid_mp ? nblk : h->grid_mp);
+  h->launches += launch_mp_init(a, grid, h->st);
+  std::vector<double> part((size_t)grid * 3);
+  int bad = 0;
+  CK(cudaMemcpyAsync(part.data(), h->partial, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(&bad, h->mp_err, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  CK(cudaGetLastError());
+  double v0[3] = {0, 0, 0};
+  for (int b = 0; b < grid; ++b)
+    for (int d = 0; d < 3; ++d) v0[d] += part[(size_t)b * 3 + d];
+  if (h->nranks > 1) {
+    CK(cudaMemcpyAsync(h->vacf_slots, v0, sizeof(v0), cudaMemcpyHostToDevice, h->st));
+    RET(allreduce(h, h->vacf_slots, 3, ncclDouble, ncclSum));
+    RET(wait_halo(h));
+    CK(cudaMemcpyAsync(v0, h->vacf_slots, sizeof(v0), cudaMemcpyDeviceToHost, h->st));
+    int badsum = bad;
+    CK(cudaMemcpyAsync(h->mp_err, &badsum, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    RET(allreduce(h, h->mp_err, 1, ncclInt32, ncclMax));
+    RET(wait_halo(h));
+    CK(cudaMemcpyAsync(&bad, h->mp_err, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    // P(now) halo planes for the first step
+    const int all3[3] = {0, 1, 2};
+    RET(halo_exchange(h, h->P[0], all3, 3, all3, 3));
+  }
+  if (vacf0)
+    for (int d = 0; d < 3; ++d) vacf0[d] = v0[d];
+  h->mp_bad = bad;
+  h->phase = PH_MP;
+  h->it = 0;
+  h->pc = 0;
+  return LBG_OK;
+}
+
+int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* converged) {
+  if (!h || nsteps < 0) return LBG_ERR_INVALID_ARG;
+  if (steps_done) *steps_done = 0;
+  if (converged) *converged = 0;
+  if (h->phase != PH_MP) return fail(h, LBG_ERR_STATE, "lbg_mp_step needs lbg_mp_init first");
+  if (nsteps == 0) return LBG_OK;
+  // the remaining fraction is static: the reference would stop in its first propagate call (:249,257)
+  if (h->mp_bad) return fail(h, LBG_ERR_RESTPART_NEGATIVE, lbg_status_string(LBG_ERR_RESTPART_NEGATIVE));
+  CK(cudaSetDevice(h->device));
+  const Geo& g = h->geo;
+  const double lim = 1.0 / (2.0 * g.lx * g.ly * h->lz_global / h->Db);
+  auto is_conv = [&](long long it, const double* v) {
+    return it > 2 && std::fabs(v[0]) < lim && std::fabs(v[1]) < lim && std::fabs(v[2]) < lim &&
+           std::fabs(v[0]) < 1.e-12 && std::fabs(v[1]) < 1.e-12 && std::fabs(v[2]) < 1.e-12;
+  };
+  int total = 0;
+  while (total < nsteps) {
+    const int chunk = (nsteps - total) < SLOT_CAP ? (nsteps - total) : SLOT_CAP;
+    CK(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
+    int pc = h->pc;
+    for (int i = 0; i < chunk; ++i) {
+      const long long it = h->it + 1 + i;
+      MPArgs a{};
+      a.geo = g;
+      a.mask = h->mask;
+      a.q = h->q;
+      a.s = h->s;
+      a.Pnow = h->P[pc];
+      a.Pnext = h->P[1 - pc];
+      a.Anow = h->A[pc];
+      a.Anext = h->A[1 - pc];
+      a.ka = h->ka;
+      a.kd = h->kd;
+      a.one_minus_kd = 1.0 - h->kd;
+      a.ads = h->ads;
+      a.partial = h->partial;
+      a.vacf_slots = h->vacf_slots;
+      a.batch_idx = i;
+      a.check_prev = (i > 0 && (it - 1) > 2) ? 1 : 0;
+      a.lim = lim;
+      a.ctrl = h->ctrl;
+      RET(wait_halo(h));
+      auto launch = [&](long long b, long long e, int accumulate) {
+        a.g_begin = b;
+        a.g_end = e;
+        a.accumulate = accumulate;
+        const long long nblk = (e - b + BLOCK - 1) / BLOCK;
+        h->launches += launch_mp_step(a, (int)(nblk < h->grid_mp ? nblk : h->grid_mp), h->st);
+      };
+      if (h->nranks == 1) {
+        launch(own_begin(h), own_end(h), 0);
+      } else {
+        const int all3[3] = {0, 1, 2};
+        launch(g.plane, 2LL * g.plane, 0);
+        if (g.nzl > 1) launch((long long)g.plane * g.nzl, (long long)g.plane * (g.nzl + 1), 1);
+        RET(halo_exchange(h, h->P[1 - pc], all3, 3, all3, 3));
+        if (g.nzl > 2) launch(2LL * g.plane, (long long)g.plane * g.nzl, 1);
+        RET(wait_halo(h));
+        RET(allreduce(h, h->vacf_slots + 3 * i, 3, ncclDouble, ncclSum));
+      }
+      pc = 1 - pc;
+    }
+    RET(wait_halo(h));
+    CK(cudaMemcpyAsync(h->h_vacf, h->vacf_slots, (size_t)chunk * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaGetLastError());
+    int executed = chunk, conv = 0;
+    for (int i = 0; i < chunk; ++i) {
+      const long long it = h->it + 1 + i;
+      if (vacf)
+        for (int d = 0; d < 3; ++d) vacf[(size_t)(total + i) * 3 + d] = h->h_vacf[(size_t)i * 3 + d];
+      if (is_conv(it, h->h_vacf + (size_t)i * 3)) {
+        executed = i + 1;
+        conv = 1;
+        break;
+      }
+    }
+    h->it += executed;
+    if (executed & 1) h->pc = 1 - h->pc;
+    total += executed;
+    if (steps_done) *steps_done = total;
+    if (conv) {
+      if (converged) *converged = 1;
+      break;
+    }
+  }
+  return LBG_OK;
+}
+
+int lbg_mp_download(lbg_handle h, double* P, double* Pads) {
+  if (!h) return LBG_ERR_INVALID_ARG;
+  if (h->phase != PH_MP) return fail(h, LBG_ERR_STATE, "lbg_mp_download needs lbg_mp_init first");
+  CK(cudaSetDevice(h->device));
+  RET(wait_halo(h));
+  double* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)h->nown * 3 * sizeof(double)));
+  double* dst[2] = {P, Pads};
+  double* src[2] = {h->P[h->pc], h->A[h->pc]};
+  for (int c = 0; c < 2; ++c) {
+    if (!dst[c]) continue;
+    h->launches += launch_soa_to_aos3(h->geo, src[c], d, h->st);
+    CK(cudaMemcpyAsync(dst[c], d, (size_t)h->nown * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+  }
+  cudaFree(d);
+  return LBG_OK;
+}
+
+// --------------------------------------------------------------------------- measurement
+int lbg_timer_start(lbg_handle h) {
+  if (!h) return LBG_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  RET(wait_halo(h));
+  CK(cudaEventRecord(h->ev_t0, h->st));
+  return LBG_OK;
+}
+
+int lbg_timer_stop(lbg_handle h, float* ms) {
+  if (!h || !ms) return LBG_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  RET(wait_halo(h));
+  CK(cudaEventRecord(h->ev_t1, h->st));
+  CK(cudaEventSynchronize(h->ev_t1));
+  CK(cudaEventElapsedTime(ms, h->ev_t0, h->ev_t1));
+  return LBG_OK;
+}
+
+int lbg_launch_count(lbg_handle h, int64_t* n) {
+  if (!h || !n) return LBG_ERR_INVALID_ARG;
+  *n = h->launches;
+  return LBG_OK;
+}
+
+int lbg_sync(lbg_handle h) {
+  if (!h) return LBG_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->st));
+  CK(cudaStreamSynchronize(h->st_comm));
+  return LBG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,516 @@
+// lb_kernels.cu -- Phase-A kernels for sm_100a: link masks, initial state,
+// the fused pull stream + moments + collide step, moments/population read-back,
+// plane profiles.
+//
+// Data layout in HBM: structure of arrays, fp64, x fastest.  Population l of
+// node g lives at f[l*nalloc + g]; g = x + lx*(y + ly*p), p = plane index in the
+// slab including one halo plane on each z side.  One thread owns one node; a
+// warp covers 32 consecutive x, so every population access of a warp is one
+// contiguous 256-byte run (the +-x neighbours are the same run shifted by 8 B).
+//
+// The step kernel K(t) implements, for fluid node r (SURVEY 8a "A2 o A3"):
+//   n(t)(r,l)   = n*(t)(r-c_l, l)   if r-c_l is fluid          [streaming, equilibration.f90:227-243]
+//               = n*(t)(r, inv l)    otherwise                  [bounce-back, equilibration.f90:204-222]
+//   rho(t), j(t), ANY(n<0), max|j(t)-j(t-1)|                    [equilibration.f90:248-300,339-343]
+//   n*(t+1)     = collide(n(t), rho(t), j(t), f)                [module_collision.f90:77-108]
+// i.e. the reference's stream of step t fused with its collide of step t+1.
+// n* is written to the other buffer (two-lattice), so a step can be redone when
+// the driver changes the force after a convergence event.
+#include <type_traits>
+
+#include "lbg_internal.h"
+
+namespace lbg {
+using namespace d3q19;
+
+namespace {
+
+template <int L, int END, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (L < END) {
+    f(std::integral_constant<int, L>{});
+    static_for<L + 1, END>(f);
+  }
+}
+
+// neighbour offsets of one node in the linear alloc index
+struct Nb {
+  int oxm, oxp, oym, oyp, ozm, ozp;
+};
+
+__device__ __forceinline__ Nb neighbours(const Geo& geo, int g) {
+  const int p = g / geo.plane;
+  const int rem = g - p * geo.plane;
+  const int y = rem / geo.lx;
+  const int x = rem - y * geo.lx;
+  Nb nb;
+  nb.oxm = (x == 0) ? (geo.lx - 1) : -1;
+  nb.oxp = (x == geo.lx - 1) ? -(geo.lx - 1) : 1;
+  nb.oym = (y == 0) ? (geo.ly - 1) * geo.lx : -geo.lx;
+  nb.oyp = (y == geo.ly - 1) ? -(geo.ly - 1) * geo.lx : geo.lx;
+  nb.ozm = (geo.zwrap && p == 1) ? (geo.nzl - 1) * geo.plane : -geo.plane;
+  nb.ozp = (geo.zwrap && p == geo.nzl) ? -(geo.nzl - 1) * geo.plane : geo.plane;
+  return nb;
+}
+
+// offset of node r + s*c_L (s = +1 or -1)
+template <int L, int S>
+__device__ __forceinline__ int offset(const Nb& nb) {
+  constexpr int X = S * cx(L), Y = S * cy(L), Z = S * cz(L);
+  int o = 0;
+  if constexpr (X > 0) o += nb.oxp;
+  if constexpr (X < 0) o += nb.oxm;
+  if constexpr (Y > 0) o += nb.oyp;
+  if constexpr (Y < 0) o += nb.oym;
+  if constexpr (Z > 0) o += nb.ozp;
+  if constexpr (Z < 0) o += nb.ozm;
+  return o;
+}
+
+// n(t)(r,·) by pull with halfway bounce-back.
+__device__ __forceinline__ void pull(const double* __restrict__ fin, long long nalloc, int g, uint32_t m, const Nb& nb,
+                                     double (&n)[NV]) {
+  static_for<0, NV>([&](auto Lc) {
+    constexpr int L = decltype(Lc)::value;
+    if constexpr (L == 0) {
+      n[0] = fin[g];
+    } else {
+      const bool src_fluid = (m >> inv(L)) & 1u;  // r - c_L == r + c_inv(L)
+      const int idx = src_fluid ? g + offset<L, -1>(nb) : g;
+      const int arr = src_fluid ? L : inv(L);
+      n[L] = fin[(long long)arr * nalloc + idx];
+    }
+  });
+}
+
+// equilibration.f90:254 and :293-300, sequential in l.
+__device__ __forceinline__ void moments(const double (&n)[NV], double fjx_half, double fjy_half, double fjz_half,
+                                        double& rho, double& jx, double& jy, double& jz, bool& negative) {
+  rho = n[0];
+  jx = fjx_half;
+  jy = fjy_half;
+  jz = fjz_half;
+  negative = n[0] < 0;
+  static_for<1, NV>([&](auto Lc) {
+    constexpr int L = decltype(Lc)::value;
+    rho = rho + n[L];
+    negative = negative || (n[L] < 0);
+    if constexpr (cx(L) > 0) jx = jx + n[L];
+    if constexpr (cx(L) < 0) jx = jx - n[L];
+    if constexpr (cy(L) > 0) jy = jy + n[L];
+    if constexpr (cy(L) < 0) jy = jy - n[L];
+    if constexpr (cz(L) > 0) jz = jz + n[L];
+    if constexpr (cz(L) < 0) jz = jz - n[L];
+  });
+}
+
+// module_collision.f90:77-108 on one fluid node, in the reference's association order.
+template <bool TAU1, bool FORCED>
+__device__ __forceinline__ void collide(double (&n)[NV], const Consts& k, double rho, double jx, double jy, double jz,
+                                        double fx, double fy, double fz, double w1, double w2, double w3) {
+  const double ux = jx / rho, uy = jy / rho, uz = jz / rho;
+  const double pxx = jx * ux, pxy = jx * uy, pxz = jx * uz;
+  const double pyx = jy * ux, pyy = jy * uy, pyz = jy * uz;
+  const double pzx = jz * ux, pzy = jz * uy, pzz = jz * uz;
+  const double qx1 = pxx * k.c1, qx0 = pxx * k.mcsq;
+  const double qy1 = pyy * k.c1, qy0 = pyy * k.mcsq;
+  const double qz1 = pzz * k.c1, qz0 = pzz * k.mcsq;
+  const double a0rho[3] = {k.a0[0] * rho, k.a0[1] * rho, k.a0[2] * rho};
+  // (c - u) * f for c in {-1, 0, +1}
+  double gx[3], gy[3], gz[3];
+  if constexpr (FORCED) {
+    gx[0] = (-1.0 - ux) * fx; gx[1] = (0.0 - ux) * fx; gx[2] = (1.0 - ux) * fx;
+    gy[0] = (-1.0 - uy) * fy; gy[1] = (0.0 - uy) * fy; gy[2] = (1.0 - uy) * fy;
+    gz[0] = (-1.0 - uz) * fz; gz[1] = (0.0 - uz) * fz; gz[2] = (1.0 - uz) * fz;
+  }
+  static_for<0, NV>([&](auto Lc) {
+    constexpr int L = decltype(Lc)::value;
+    constexpr int X = cx(L), Y = cy(L), Z = cz(L), K = kind(L);
+    const double cj = cdot<L>(jx, jy, jz);
+    double br = X ? qx1 : qx0;
+    if constexpr (X && Y) br = br + (X * Y > 0 ? pxy : -pxy);
+    if constexpr (X && Z) br = br + (X * Z > 0 ? pxz : -pxz);
+    if constexpr (Y && X) br = br + (Y * X > 0 ? pyx : -pyx);
+    br = br + (Y ? qy1 : qy0);
+    if constexpr (Y && Z) br = br + (Y * Z > 0 ? pyz : -pyz);
+    if constexpr (Z && X) br = br + (Z * X > 0 ? pzx : -pzx);
+    if constexpr (Z && Y) br = br + (Z * Y > 0 ? pzy : -pzy);
+    br = br + (Z ? qz1 : qz0);
+    const double neq = (a0rho[K] + k.a1[K] * cj) + k.a2[K] * br;
+    double v;
+    if constexpr (TAU1) v = neq;  // w1 == 0, w2 == 1: 0*n + 1*neq == neq
+    else v = w1 * n[L] + w2 * neq;
+    if constexpr (FORCED) {
+      const double g1 = (gx[X + 1] + gy[Y + 1]) + gz[Z + 1];
+      const double cu = cdot<L>(ux, uy, uz);
+      const double cf = cdot<L>(fx, fy, fz);
+      const double force = k.a1[K] * g1 + (k.two_a2[K] * cu) * cf;
+      v = v + w3 * force;
+    }
+    n[L] = v;
+  });
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+template <bool TAU1, int FMODE, bool CHECK, bool WRITEJ>
+__global__ void __launch_bounds__(BLOCK) lb_step_kernel(const __grid_constant__ LBArgs a) {
+  __shared__ int s_stop;
+  __shared__ double s_red[BLOCK / 32];
+  __shared__ int s_neg;
+  if (threadIdx.x == 0) {
+    int stop = *(volatile int*)&a.ctrl->stop | *(volatile int*)&a.ctrl->neg_step_idx;
+    if (!stop && a.prev_checked && a.prev_may_stop) {
+      const double prev = __longlong_as_double((long long)*(volatile unsigned long long*)&a.l2_slots[a.batch_idx - 1]);
+      if (prev <= a.target) {  // equilibration.f90:346
+        a.ctrl->stop = 1;
+        a.ctrl->stop_idx = a.batch_idx;  // 1 + index of the converged step
+        stop = 1;
+      }
+    }
+    s_stop = stop;
+    s_neg = 0;
+  }
+  __syncthreads();
+  if (s_stop) return;
+
+  const Geo& geo = a.geo;
+  const long long nalloc = geo.nalloc;
+  double dmax = 0.0;
+  bool any_neg = false;
+  for (long long gg = a.g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; gg < a.g_end;
+       gg += (long long)gridDim.x * BLOCK) {
+    const int g = (int)gg;
+    const uint32_t m = __ldg(a.mask + g);
+    if (!(m & MASK_FLUID)) continue;
+    const Nb nb = neighbours(geo, g);
+    double n[NV];
+    pull(a.fin, nalloc, g, m, nb, n);
+    double fjx = 0, fjy = 0, fjz = 0, fcx = 0, fcy = 0, fcz = 0;
+    if constexpr (FMODE == FORCE_UNIFORM) {
+      fjx = a.fj[0]; fjy = a.fj[1]; fjz = a.fj[2];
+      fcx = a.fc[0]; fcy = a.fc[1]; fcz = a.fc[2];
+    } else if constexpr (FMODE == FORCE_FIELD) {
+      fjx = a.fj_field[g]; fjy = a.fj_field[nalloc + g]; fjz = a.fj_field[2 * nalloc + g];
+      fcx = a.fc_field[g]; fcy = a.fc_field[nalloc + g]; fcz = a.fc_field[2 * nalloc + g];
+    }
+    double rho, jx, jy, jz;
+    bool neg;
+    moments(n, fjx / 2.0, fjy / 2.0, fjz / 2.0, rho, jx, jy, jz, neg);
+    any_neg |= neg;
+    if constexpr (CHECK) {
+      const double ox = a.jold[g], oy = a.jold[nalloc + g], oz = a.jold[2 * nalloc + g];
+      dmax = fmax(dmax, fmax(fabs(jx - ox), fmax(fabs(jy - oy), fabs(jz - oz))));
+    }
+    if constexpr (WRITEJ) {
+      a.jnew[g] = jx;
+      a.jnew[nalloc + g] = jy;
+      a.jnew[2 * nalloc + g] = jz;
+    }
+    collide<TAU1, FMODE != FORCE_NONE>(n, a.k, rho, jx, jy, jz, fcx, fcy, fcz, a.w1, a.w2, a.w3);
+    static_for<0, NV>([&](auto Lc) {
+      constexpr int L = decltype(Lc)::value;
+      a.fout[(long long)L * nalloc + g] = n[L];
+    });
+  }
+  if (any_neg) s_neg = 1;
+  if constexpr (CHECK) {
+    dmax = warp_max(dmax);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = dmax;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if constexpr (CHECK) {
+      double v = s_red[0];
+#pragma unroll
+      for (int w = 1; w < BLOCK / 32; ++w) v = fmax(v, s_red[w]);
+      // non-negative doubles order like their bit patterns
+      atomicMax(&a.l2_slots[a.batch_idx], (unsigned long long)__double_as_longlong(v));
+    }
+    if (s_neg) atomicCAS(&a.ctrl->neg_step_idx, 0, a.batch_idx + 1);
+  }
+}
+
+template <bool TAU1, int FMODE>
+__global__ void __launch_bounds__(BLOCK) collide_kernel(const __grid_constant__ CollideArgs a) {
+  const long long nalloc = a.geo.nalloc;
+  for (long long gg = a.g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; gg < a.g_end;
+       gg += (long long)gridDim.x * BLOCK) {
+    const int g = (int)gg;
+    const uint32_t m = __ldg(a.mask + g);
+    double n[NV];
+    static_for<0, NV>([&](auto Lc) {
+      constexpr int L = decltype(Lc)::value;
+      n[L] = a.fin[(long long)L * nalloc + g];
+    });
+    if (m & MASK_FLUID) {
+      double fcx = 0, fcy = 0, fcz = 0;
+      if constexpr (FMODE == FORCE_UNIFORM) {
+        fcx = a.fc[0]; fcy = a.fc[1]; fcz = a.fc[2];
+      } else if constexpr (FMODE == FORCE_FIELD) {
+        fcx = a.fc_field[g]; fcy = a.fc_field[nalloc + g]; fcz = a.fc_field[2 * nalloc + g];
+      }
+      collide<TAU1, FMODE != FORCE_NONE>(n, a.k, a.mom[g], a.mom[nalloc + g], a.mom[2 * nalloc + g],
+                                         a.mom[3 * nalloc + g], fcx, fcy, fcz, a.w1, a.w2, a.w3);
+    }
+    static_for<0, NV>([&](auto Lc) {
+      constexpr int L = decltype(Lc)::value;
+      a.fout[(long long)L * nalloc + g] = n[L];
+    });
+  }
+}
+
+template <int FMODE>
+__global__ void __launch_bounds__(BLOCK) moments_kernel(const __grid_constant__ MomArgs a) {
+  const long long nalloc = a.geo.nalloc;
+  for (long long gg = a.g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; gg < a.g_end;
+       gg += (long long)gridDim.x * BLOCK) {
+    const int g = (int)gg;
+    const uint32_t m = __ldg(a.mask + g);
+    double n[NV];
+    double rho = 0, jx = 0, jy = 0, jz = 0;
+    if (m & MASK_FLUID) {
+      const Nb nb = neighbours(a.geo, g);
+      pull(a.fin, nalloc, g, m, nb, n);
+      double fjx = 0, fjy = 0, fjz = 0;
+      if constexpr (FMODE == FORCE_UNIFORM) {
+        fjx = a.fj[0]; fjy = a.fj[1]; fjz = a.fj[2];
+      } else if constexpr (FMODE == FORCE_FIELD) {
+        fjx = a.fj_field[g]; fjy = a.fj_field[nalloc + g]; fjz = a.fj_field[2 * nalloc + g];
+      }
+      bool neg;
+      moments(n, fjx / 2.0, fjy / 2.0, fjz / 2.0, rho, jx, jy, jz, neg);
+    } else {
+      static_for<0, NV>([&](auto Lc) { n[decltype(Lc)::value] = 0.0; });
+    }
+    if (a.mom) {
+      a.mom[g] = rho;
+      a.mom[nalloc + g] = jx;
+      a.mom[2 * nalloc + g] = jy;
+      a.mom[3 * nalloc + g] = jz;
+    }
+    if (a.pops) {
+      static_for<0, NV>([&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        a.pops[(long long)L * nalloc + g] = n[L];
+      });
+    }
+  }
+}
+
+// supercell_definition.f90:115-147 + the neighbour tables of equilibration.f90:109-119,
+// folded into one word per node.  nature has valid halo planes.
+__global__ void __launch_bounds__(BLOCK) build_mask_kernel(Geo geo, const int8_t* __restrict__ nat,
+                                                           uint32_t* __restrict__ mask) {
+  const long long g_begin = geo.plane, g_end = (long long)geo.plane * (geo.nzl + 1);
+  for (long long gg = g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; gg < g_end;
+       gg += (long long)gridDim.x * BLOCK) {
+    const int g = (int)gg;
+    Geo gz = geo;
+    gz.zwrap = 0;  // nature carries real halo planes
+    const Nb nb = neighbours(gz, g);
+    const int8_t me = nat[g];
+    uint32_t m = (me == 0) ? MASK_FLUID : 0u;
+    bool interfacial = false;
+    static_for<1, NV>([&](auto Lc) {
+      constexpr int L = decltype(Lc)::value;
+      const int8_t other = nat[g + offset<L, +1>(nb)];
+      if (other == 0) m |= (1u << L);
+      interfacial = interfacial || (other != me);
+    });
+    if (interfacial) m |= MASK_INTERFACIAL;
+    mask[g] = m;
+  }
+}
+
+// init_simu.f90:24-39 and equilibration.f90:59,75-80
+__global__ void __launch_bounds__(BLOCK) lb_init_kernel(Geo geo, const uint32_t* __restrict__ mask, double rho0,
+                                                        double a00, double a01, double a02, double* __restrict__ f,
+                                                        double* __restrict__ mom) {
+  const long long g_begin = geo.plane, g_end = (long long)geo.plane * (geo.nzl + 1);
+  const double a0[3] = {a00, a01, a02};
+  for (long long g = g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; g < g_end;
+       g += (long long)gridDim.x * BLOCK) {
+    const double dens = (mask[g] & MASK_FLUID) ? rho0 : 0.0;
+    static_for<0, NV>([&](auto Lc) {
+      constexpr int L = decltype(Lc)::value;
+      f[(long long)L * geo.nalloc + g] = dens * a0[kind(L)];
+    });
+    mom[g] = dens;
+    mom[geo.nalloc + g] = 0.0;
+    mom[2 * geo.nalloc + g] = 0.0;
+    mom[3 * geo.nalloc + g] = 0.0;
+  }
+}
+
+// equilibration.f90:381-386 materialised as a field (used when a uniform force
+// and a force field meet across a force change).
+__global__ void __launch_bounds__(BLOCK) fill_force_kernel(Geo geo, const uint32_t* __restrict__ mask, double fx,
+                                                           double fy, double fz, double* __restrict__ field) {
+  const long long g_begin = geo.plane, g_end = (long long)geo.plane * (geo.nzl + 1);
+  for (long long g = g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; g < g_end;
+       g += (long long)gridDim.x * BLOCK) {
+    const bool fl = mask[g] & MASK_FLUID;
+    field[g] = fl ? fx : 0.0;
+    field[geo.nalloc + g] = fl ? fy : 0.0;
+    field[2 * geo.nalloc + g] = fl ? fz : 0.0;
+  }
+}
+
+// equilibration.f90:161-172: one block per row along `axis`; fixed-order tree, so deterministic.
+__global__ void __launch_bounds__(BLOCK) profile_kernel(const __grid_constant__ ProfileArgs a) {
+  const Geo& geo = a.geo;
+  const int p = blockIdx.x;
+  const int n1 = a.axis == 0 ? geo.ly : geo.lx;
+  const int n2 = a.axis == 2 ? geo.ly : geo.nzl;
+  double sx = 0, sy = 0, sz = 0, sd = 0, cnt = 0;
+  for (long long q = threadIdx.x; q < (long long)n1 * n2; q += BLOCK) {
+    const int b = (int)(q / n1), c = (int)(q - (long long)b * n1);
+    const int i = a.axis == 0 ? p : c;
+    const int j = a.axis == 0 ? c : (a.axis == 1 ? p : b);
+    const int kk = a.axis == 2 ? p : b;
+    const long long g = (long long)i + (long long)geo.lx * j + (long long)geo.plane * (kk + 1);
+    const double d = a.mom[g];
+    sd += d;
+    sx += a.mom[geo.nalloc + g];
+    sy += a.mom[2 * geo.nalloc + g];
+    sz += a.mom[3 * geo.nalloc + g];
+    cnt += (d > a.eps) ? 1.0 : 0.0;
+  }
+  __shared__ double red[5][BLOCK];
+  red[0][threadIdx.x] = sx; red[1][threadIdx.x] = sy; red[2][threadIdx.x] = sz;
+  red[3][threadIdx.x] = sd; red[4][threadIdx.x] = cnt;
+  __syncthreads();
+  for (int s = BLOCK / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int v = 0; v < 5; ++v) red[v][threadIdx.x] += red[v][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x < 5) a.out[(long long)p * 5 + threadIdx.x] = red[threadIdx.x][0];
+}
+
+__global__ void __launch_bounds__(BLOCK) count_flags_kernel(Geo geo, const uint32_t* __restrict__ mask,
+                                                            unsigned long long* counts) {
+  const long long g_begin = geo.plane, g_end = (long long)geo.plane * (geo.nzl + 1);
+  unsigned int nf = 0, nif = 0;
+  for (long long g = g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; g < g_end;
+       g += (long long)gridDim.x * BLOCK) {
+    const uint32_t m = mask[g];
+    if (m & MASK_FLUID) {
+      ++nf;
+      if (m & MASK_INTERFACIAL) ++nif;
+    }
+  }
+  nf = __reduce_add_sync(0xffffffffu, nf);
+  nif = __reduce_add_sync(0xffffffffu, nif);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&counts[0], (unsigned long long)nf);
+    atomicAdd(&counts[1], (unsigned long long)nif);
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK) extract_flag_kernel(Geo geo, const uint32_t* __restrict__ mask, uint32_t bit,
+                                                             int8_t* __restrict__ out) {
+  const long long nown = (long long)geo.plane * geo.nzl;
+  for (long long q = (long long)blockIdx.x * BLOCK + threadIdx.x; q < nown; q += (long long)gridDim.x * BLOCK)
+    out[q] = (mask[q + geo.plane] & bit) ? 1 : 0;
+}
+
+inline int small_grid(long long n) {
+  long long b = (n + BLOCK - 1) / BLOCK;
+  return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
+}
+
+}  // namespace
+
+int launch_build_mask(const Geo& g, const int8_t* nature_halo, uint32_t* mask, cudaStream_t st) {
+  build_mask_kernel<<<small_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, nature_halo, mask);
+  return 1;
+}
+
+int launch_lb_init(const Geo& g, const uint32_t* mask, double rho0, const double a0[3], double* f, double* mom,
+                   cudaStream_t st) {
+  lb_init_kernel<<<small_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, mask, rho0, a0[0], a0[1], a0[2], f, mom);
+  return 1;
+}
+
+int launch_fill_force(const Geo& g, const uint32_t* mask, const double f[3], double* field, cudaStream_t st) {
+  fill_force_kernel<<<small_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, mask, f[0], f[1], f[2], field);
+  return 1;
+}
+
+int launch_count_flags(const Geo& g, const uint32_t* mask, unsigned long long* counts2, cudaStream_t st) {
+  count_flags_kernel<<<small_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, mask, counts2);
+  return 1;
+}
+
+int launch_extract_flag(const Geo& g, const uint32_t* mask, uint32_t bit, int8_t* out_own, cudaStream_t st) {
+  extract_flag_kernel<<<small_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, mask, bit, out_own);
+  return 1;
+}
+
+int launch_profile(const ProfileArgs& a, int rows, cudaStream_t st) {
+  profile_kernel<<<rows, BLOCK, 0, st>>>(a);
+  return 1;
+}
+
+namespace {
+template <bool TAU1, int FMODE>
+void launch_step_cw(const LBArgs& a, bool check, bool writej, int grid, cudaStream_t st) {
+  if (check) lb_step_kernel<TAU1, FMODE, true, true><<<grid, BLOCK, 0, st>>>(a);
+  else if (writej) lb_step_kernel<TAU1, FMODE, false, true><<<grid, BLOCK, 0, st>>>(a);
+  else lb_step_kernel<TAU1, FMODE, false, false><<<grid, BLOCK, 0, st>>>(a);
+}
+template <bool TAU1>
+void launch_step_f(const LBArgs& a, int fmode, bool check, bool writej, int grid, cudaStream_t st) {
+  if (fmode == FORCE_NONE) launch_step_cw<TAU1, FORCE_NONE>(a, check, writej, grid, st);
+  else if (fmode == FORCE_UNIFORM) launch_step_cw<TAU1, FORCE_UNIFORM>(a, check, writej, grid, st);
+  else launch_step_cw<TAU1, FORCE_FIELD>(a, check, writej, grid, st);
+}
+template <bool TAU1>
+void launch_collide_f(const CollideArgs& a, int fmode, int grid, cudaStream_t st) {
+  if (fmode == FORCE_NONE) collide_kernel<TAU1, FORCE_NONE><<<grid, BLOCK, 0, st>>>(a);
+  else if (fmode == FORCE_UNIFORM) collide_kernel<TAU1, FORCE_UNIFORM><<<grid, BLOCK, 0, st>>>(a);
+  else collide_kernel<TAU1, FORCE_FIELD><<<grid, BLOCK, 0, st>>>(a);
+}
+int clamp_grid(long long n, int grid) {
+  const long long b = (n + BLOCK - 1) / BLOCK;
+  return (int)(b < 1 ? 1 : (b < grid ? b : grid));
+}
+}  // namespace
+
+int launch_lb_step(const LBArgs& a, bool tau1, int fmode, bool check, bool writej, int grid, cudaStream_t st) {
+  const int gr = clamp_grid(a.g_end - a.g_begin, grid);
+  if (tau1) launch_step_f<true>(a, fmode, check, writej, gr, st);
+  else launch_step_f<false>(a, fmode, check, writej, gr, st);
+  return 1;
+}
+
+int launch_collide(const CollideArgs& a, bool tau1, int fmode, int grid, cudaStream_t st) {
+  const int gr = clamp_grid(a.g_end - a.g_begin, grid);
+  if (tau1) launch_collide_f<true>(a, fmode, gr, st);
+  else launch_collide_f<false>(a, fmode, gr, st);
+  return 1;
+}
+
+int launch_moments(const MomArgs& a, int fmode, int grid, cudaStream_t st) {
+  const int gr = clamp_grid(a.g_end - a.g_begin, grid);
+  if (fmode == FORCE_NONE) moments_kernel<FORCE_NONE><<<gr, BLOCK, 0, st>>>(a);
+  else if (fmode == FORCE_UNIFORM) moments_kernel<FORCE_UNIFORM><<<gr, BLOCK, 0, st>>>(a);
+  else moments_kernel<FORCE_FIELD><<<gr, BLOCK, 0, st>>>(a);
+  return 1;
+}
+
+int occupancy_grid_lb(int sm_count) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lb_step_kernel<true, FORCE_UNIFORM, true, true>, BLOCK, 0);
+  if (per_sm < 1) per_sm = 1;
+  return sm_count * per_sm;
+}
+
+}  // namespace lbg

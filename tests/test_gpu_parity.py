@@ -1,0 +1,360 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerance: north_star asks for 1e-12 relative in fp64 (the allowed difference
+being summation order of cross-node sums).  Per-node quantities (populations,
+density, momentum, P, Pads, interfacial flags, l2err, exit step) are expected
+to be *bit-identical* and are tested with array_equal; cross-node sums (vacf,
+profiles, total flux) are tested at RTOL = 1e-12 relative to the field scale.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.util import GOLDEN, RTOL, random_nature, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu():
+    import laboetie_b200 as lb
+    return lb
+
+
+GEOMS = [
+    ("rand6x5x7", lambda: random_nature(6, 5, 7, 0.3, 1)),
+    ("line1x1x22", lambda: random_nature(1, 1, 22, 0.1, 2)),
+    ("rand4x4x4", lambda: random_nature(4, 4, 4, 0.5, 3)),
+    ("rand2x3x2", lambda: random_nature(2, 3, 2, 0.3, 4)),
+    ("rand33x7x5", lambda: random_nature(33, 7, 5, 0.25, 7)),
+    ("rand70x3x4", lambda: random_nature(70, 3, 4, 0.2, 8)),
+    ("plane1x12x9", lambda: random_nature(1, 12, 9, 0.2, 5)),
+    ("row7x1x3", lambda: random_nature(7, 1, 3, 0.25, 6)),
+    ("slit8x8x16", lambda: O.geometry(1, 8, 8, 16)),
+    ("cyl11x11x4", lambda: O.geometry(2, 11, 11, 4)),
+    ("bcc12", lambda: O.geometry(3, 12, 12, 12)),
+    ("bulk5x4x3", lambda: O.geometry(-1, 5, 4, 3)),
+]
+
+
+@pytest.mark.parametrize("name,mk", GEOMS, ids=[g[0] for g in GEOMS])
+def test_interfacial_flags_and_counts(name, mk):
+    lb = _gpu()
+    nat = mk()
+    with lb.LaboetieGPU(nat) as sim:
+        itf = sim.interfacial()
+        ref = O.detect_interfacial(nat)
+        assert np.array_equal(itf, ref)
+        nf, nif = sim.counts()
+        assert nf == int((nat == 0).sum()) and nif == int(((nat == 0) & (ref == 1)).sum())
+
+
+@pytest.mark.parametrize("tau", [1.0, 0.8])
+@pytest.mark.parametrize("name,mk", GEOMS, ids=[g[0] for g in GEOMS])
+def test_lb_steps_bit_exact(name, mk, tau):
+    """check_every=1, force switched on after step 3 (as the driver does), populations read back."""
+    lb = _gpu()
+    nat = mk()
+    f = [1e-3, -2e-3, 5e-4]
+    st = O.LBState(nat, 1.0, tau)
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_init(1.0)
+        assert np.array_equal(sim.lb_populations(), st.n)
+        ref_hist = []
+        for _ in range(3):
+            ref_hist.append(st.step()[1])
+        done, conv, h = sim.lb_step(3, tau=tau, check_every=1, target_error=-1.0)
+        assert done == 3 and not conv
+        assert np.array_equal(h, np.array(ref_hist))
+        assert np.array_equal(sim.lb_populations(), st.n)
+        st.set_force_uniform(f)
+        sim.lb_set_force_uniform(f)
+        ref_hist = [st.step()[1] for _ in range(9)]
+        done, conv, h = sim.lb_step(9, tau=tau, check_every=1, target_error=-1.0)
+        assert done == 9 and sim.t == 12
+        assert np.array_equal(h, np.array(ref_hist))
+        rho, jx, jy, jz = sim.lb_moments()
+        assert np.array_equal(rho, st.rho) and np.array_equal(jx, st.jx)
+        assert np.array_equal(jy, st.jy) and np.array_equal(jz, st.jz)
+        n = sim.lb_populations()
+        assert rel_err(n, st.n) <= RTOL
+        assert np.array_equal(n, st.n)
+        assert (n[:, nat == 1] == 0).all()
+        # a further step after the read-back (exercises the redo path)
+        e = st.step()[1]
+        done, conv, h = sim.lb_step(1, tau=tau, check_every=1, target_error=-1.0)
+        assert h[0] == e and np.array_equal(sim.lb_populations(), st.n)
+
+
+def test_check_every_variants_agree():
+    """check_every = 0 / 4 / 1 give the same populations; l2err values on checked steps coincide."""
+    lb = _gpu()
+    nat = random_nature(9, 6, 5, 0.25, 21)
+    outs = []
+    for ce in (1, 4, 0):
+        with lb.LaboetieGPU(nat) as sim:
+            sim.lb_init(1.0)
+            sim.lb_set_force_uniform([1e-4, 0, 2e-4])
+            done, conv, h = sim.lb_step(17, tau=0.9, check_every=ce, target_error=-1.0)
+            assert done == 17 and not conv
+            outs.append((sim.lb_populations(), h))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][0], outs[2][0])
+    h1, h4, h0 = outs[0][1], outs[1][1], outs[2][1]
+    assert np.isnan(h0).all()
+    for i in range(17):
+        if (i + 1) % 4 == 0:
+            assert h4[i] == h1[i]
+        else:
+            assert np.isnan(h4[i])
+
+
+def test_force_field_and_upload_paths():
+    lb = _gpu()
+    nat = random_nature(7, 6, 5, 0.3, 31)
+    rng = np.random.default_rng(5)
+    fl = nat == 0
+    fx, fy, fz = (np.where(fl, rng.normal(0, 1e-4, nat.shape), 0.0) for _ in range(3))
+    st = O.LBState(nat, 1.0, 0.7)
+    for _ in range(4):
+        st.step()
+    with lb.LaboetieGPU(nat) as sim:
+        # restart from a host state, then switch to a per-node force field (compensate_f_ext style)
+        sim.lb_upload(st.n, st.rho, st.jx, st.jy, st.jz)
+        st.fx[...], st.fy[...], st.fz[...] = fx, fy, fz
+        sim.lb_set_force_field(fx, fy, fz)
+        ref = [st.step()[1] for _ in range(6)]
+        done, conv, h = sim.lb_step(6, tau=0.7, check_every=1, target_error=-1.0)
+        assert np.array_equal(h, np.array(ref))
+        assert np.array_equal(sim.lb_populations(), st.n)
+        # back to a uniform force: j(t) keeps the field's f/2, the collision takes the new one
+        st.fx[...], st.fy[...], st.fz[...] = 0, 0, 0
+        st.set_force_uniform([2e-4, 0, 0])
+        sim.lb_set_force_uniform([2e-4, 0, 0])
+        ref = [st.step()[1] for _ in range(3)]
+        done, conv, h = sim.lb_step(3, tau=0.7, check_every=1, target_error=-1.0)
+        assert np.array_equal(h, np.array(ref))
+        assert np.array_equal(sim.lb_populations(), st.n)
+        rho, jx, jy, jz = sim.lb_moments()
+        assert np.array_equal(jx, st.jx) and np.array_equal(rho, st.rho)
+
+
+def test_equilibration_exit_steps_match_reference_semantics():
+    """Stock lb.in leaves the loop at t=4; a forced slit reproduces exit step and l2err history."""
+    lb = _gpu()
+    from laboetie_b200 import driver
+    nat = O.geometry(1, 1, 1, 102)
+    with lb.LaboetieGPU(nat) as sim:
+        r = driver.equilibration(sim, [0, 0, 0])
+        assert r["rc"] == 0 and r["t_exit"] == 4 and r["t_fext"] == 4 and (r["l2err"] == 0).all()
+    nat = O.geometry(1, 3, 2, 14)
+    ref = O.equilibration(nat, [1e-5, 0, 0], tau=1.0, target_error=1e-10)
+    with lb.LaboetieGPU(nat) as sim:
+        r = driver.equilibration(sim, [1e-5, 0, 0], tau=1.0, target_error=1e-10, chunk=97)
+        assert (r["t_exit"], r["t_fext"]) == (ref["t_exit"], ref["t_fext"])
+        assert np.array_equal(r["l2err"], ref["l2err"])
+        rho, jx, jy, jz = sim.lb_moments()
+        assert np.array_equal(jx, ref["jx"]) and np.array_equal(rho, ref["rho"])
+        assert np.array_equal(sim.lb_populations(), ref["n"])
+
+
+def test_tuto_config1_flow_and_tracers():
+    """BASELINE config 1: tuto 1x50x50 one-disk geometry, flow equilibration then moment propagation."""
+    lb = _gpu()
+    from laboetie_b200 import driver
+    import os
+    nat = O.read_geom_in(os.path.join(GOLDEN, "geom.in_chromat_1disks-dia10-1x50x50_v1"), 1, 50, 50)
+    f = [0.0, 1e-5, 0.0]
+    g = np.load(os.path.join(GOLDEN, "tuto_cfg1_oracle.npz"))
+    with lb.LaboetieGPU(nat) as sim:
+        r = driver.equilibration(sim, f, tau=1.0, target_error=1e-10)
+        assert r["t_exit"] == int(g["t_exit"]) and r["t_fext"] == int(g["t_fext"])
+        assert np.array_equal(r["l2err"], g["l2err"])
+        rho, jx, jy, jz = sim.lb_moments()
+        assert np.array_equal(rho, g["rho"]) and np.array_equal(jy, g["jy"]) and np.array_equal(jz, g["jz"])
+        prof = sim.lb_profiles(2)
+        assert rel_err(prof, g["prof_z"]) <= RTOL
+        d = driver.drop_tracers(sim, f, 0.01, 0.1, 0.01, max_steps=int(g["mp_steps"]))
+        P, A = sim.mp_download()
+        assert np.array_equal(P, g["P"]) and np.array_equal(A, g["Pads"])
+        scale = np.abs(g["vacf"]).max(axis=0)
+        assert (np.abs(d["vacf"] - g["vacf"]) <= RTOL * scale).all()
+
+
+@pytest.mark.parametrize("ka,kd", [(0.1, 0.01), (0.0, 0.0), (0.05, 0.0)])
+@pytest.mark.parametrize("name,mk", GEOMS[:9], ids=[g[0] for g in GEOMS[:9]])
+def test_moment_propagation_bit_exact(name, mk, ka, kd):
+    lb = _gpu()
+    nat = mk()
+    itf = O.detect_interfacial(nat)
+    f = [1e-4, 2e-4, -1e-4]
+    st = O.LBState(nat)
+    for _ in range(3):
+        st.step()
+    st.set_force_uniform(f)
+    for _ in range(12):
+        st.step()
+    Db = 0.01
+    mp = O.MPState(nat, itf, st.rho, st.jx, st.jy, st.jz, f, Db, ka, kd)
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_init(1.0)
+        sim.lb_step(3, check_every=0)
+        sim.lb_set_force_uniform(f)
+        sim.lb_step(12, check_every=0)
+        v0 = sim.mp_init(Db, ka, kd, f)
+        assert rel_err(v0, mp.vacf0) <= RTOL
+        P, A = sim.mp_download()
+        assert np.array_equal(P, mp.P[0]) and (A == 0).all()
+        ref_v = []
+        for _ in range(21):
+            rc, v, conv = mp.propagate()
+            assert rc == 0
+            ref_v.append(v)
+        done, conv, v = sim.mp_step(21)
+        assert done == 21
+        P, A = sim.mp_download()
+        assert np.array_equal(P, mp.P[0])
+        assert np.array_equal(A, mp.Pads[0])
+        ref_v = np.array(ref_v)
+        scale = np.maximum(np.abs(ref_v).max(axis=0), 1e-300)
+        assert (np.abs(v - ref_v) <= RTOL * scale).all()
+
+
+def test_mp_convergence_step_matches():
+    """Bulk fluid at rest: vacf(t>=1) = 0, so propagate reports convergence at it=3 (it>2, :284)."""
+    lb = _gpu()
+    from laboetie_b200 import driver
+    nat = O.geometry(-1, 4, 5, 3)
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_init(1.0)
+        d = driver.drop_tracers(sim, [0, 0, 0], 0.0123, 0.0, 0.0, max_steps=-1, chunk=50)
+        assert d["converged"] and d["steps"] == 3
+        assert np.allclose(d["vacf"][0], 2 * 0.0123, rtol=1e-13)
+        assert np.abs(d["vacf"][1:]).max() < 1e-17
+
+
+def test_profiles_flux_probe():
+    lb = _gpu()
+    nat = random_nature(9, 7, 6, 0.3, 41)
+    st = O.LBState(nat, 1.0, 0.9)
+    st.set_force_uniform([1e-3, 2e-3, -1e-3])
+    for _ in range(8):
+        st.step()
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_init(1.0)
+        sim.lb_set_force_uniform([1e-3, 2e-3, -1e-3])
+        sim.lb_step(8, tau=0.9, check_every=0)
+        for axis in range(3):
+            ref = O.profiles(st.rho, st.jx, st.jy, st.jz, axis)
+            got = sim.lb_profiles(axis)
+            for c in range(4):
+                assert rel_err(got[:, c], ref[:, c]) <= RTOL
+        assert rel_err(sim.lb_total_flux(), O.total_flux(st.jx, st.jy, st.jz)) <= RTOL
+        i, j, k = 3, 2, 4
+        assert np.array_equal(sim.lb_probe(i, j, k), [st.jx[k, j, i], st.jy[k, j, i], st.jz[k, j, i], st.rho[k, j, i]])
+
+
+def test_error_codes_mirror_reference_stops():
+    lb = _gpu()
+    nat = O.geometry(1, 4, 4, 8)
+    with pytest.raises(lb.LbgError) as e:
+        lb.LaboetieGPU(np.ones((3, 3, 3), np.int8))
+    assert e.value.status == 6                      # all solid
+    with lb.LaboetieGPU(nat) as sim:
+        with pytest.raises(lb.LbgError) as e:
+            sim.lb_step(1)
+        assert e.value.status == 8                  # no lb_init yet
+        sim.lb_init(1.0)
+        with pytest.raises(lb.LbgError) as e:
+            sim.lb_step(1, tau=0.4)
+        assert e.value.status == 3                  # relaxation_time < 0.5
+        with pytest.raises(lb.LbgError) as e:
+            sim.mp_init(0.0, 0.1, 0.01, [0, 0, 0])
+        assert e.value.status == 4                  # tracer_Db invalid
+        with pytest.raises(lb.LbgError) as e:
+            sim.mp_init(0.01, -0.1, 0.01, [0, 0, 0])
+        assert e.value.status == 5
+        # a huge force drives populations negative: the reference ERROR STOPs at that step
+        st = O.LBState(nat)
+        st.set_force_uniform([0.9, 0, 0])
+        t_neg = None
+        for t in range(1, 20):
+            rc, _ = st.step()
+            if rc:
+                t_neg = t
+                break
+        assert t_neg is not None
+        sim.lb_set_force_uniform([0.9, 0, 0])
+        with pytest.raises(lb.LbgError) as e:
+            sim.lb_step(50, check_every=1, target_error=-1.0)
+        assert e.value.status == 1 and sim.last_steps_done == t_neg
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_init(1.0)
+        sim.mp_init(0.01, 0.95, 0.5, [0, 0, 0])     # ka so large that the remaining fraction goes negative
+        with pytest.raises(lb.LbgError) as e:
+            sim.mp_step(1)
+        assert e.value.status == 2
+        with pytest.raises(lb.LbgError) as e:
+            sim.lb_step(1)
+        assert e.value.status == 8                  # populations were released by mp_init
+
+
+def test_medium_lattice_against_oracle():
+    """64x64x32 slit (config 2 cross-section): 20 LB + 20 MP steps against the oracle."""
+    lb = _gpu()
+    nat = O.geometry(1, 64, 64, 32)
+    itf = O.detect_interfacial(nat)
+    f = [1e-6, 0, 0]
+    st = O.LBState(nat)
+    st.set_force_uniform(f)
+    ref = [st.step()[1] for _ in range(20)]
+    mp = O.MPState(nat, itf, st.rho, st.jx, st.jy, st.jz, f, 0.01, 0.1, 0.01)
+    ref_v = np.array([mp.propagate()[1] for _ in range(20)])
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_init(1.0)
+        sim.lb_set_force_uniform(f)
+        done, conv, h = sim.lb_step(20, check_every=1, target_error=-1.0)
+        assert np.array_equal(h, np.array(ref))
+        assert np.array_equal(sim.lb_populations(), st.n)
+        v0 = sim.mp_init(0.01, 0.1, 0.01, f)
+        assert rel_err(v0, mp.vacf0) <= RTOL
+        done, conv, v = sim.mp_step(20)
+        P, A = sim.mp_download()
+        assert np.array_equal(P, mp.P[0]) and np.array_equal(A, mp.Pads[0])
+        assert (np.abs(v - ref_v) <= RTOL * np.abs(ref_v).max(axis=0) + 1e-300).all()
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 at full size (64x64x256 slit): size-independent properties."""
+    lb = _gpu()
+    nat = O.geometry(1, 64, 64, 256)
+    f = [1e-6, 0, 0]
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_init(1.0)
+        sim.lb_set_force_uniform(f)
+        sim.lb_step(200, check_every=0)
+        n = sim.lb_populations()
+        rho, jx, jy, jz = sim.lb_moments()
+        nf = int((nat == 0).sum())
+        assert (n[:, nat == 1] == 0).all()                      # solid populations stay 0
+        assert n.min() >= 0
+        assert abs(n.sum() - nf) <= 1e-12 * nf                  # mass conservation
+        # translation invariance in x and y of the slit: every (x,y) column is identical
+        assert np.array_equal(jx, np.broadcast_to(jx[:, :1, :1], jx.shape))
+        assert np.abs(jy).max() == 0 and np.abs(jz).max() < 1e-18
+        # momentum balance: d/dt sum(jx) -> 0 as the Poiseuille profile builds; sign and symmetry in z
+        prof = sim.lb_profiles(2)[:, 0]
+        assert (prof[1:-1] > 0).all() and prof[0] == 0 and prof[-1] == 0
+        assert np.allclose(prof, prof[::-1], rtol=1e-12, atol=0)
+        v0 = sim.mp_init(0.01, 0.1, 0.01, f)
+        P0, A0 = sim.mp_download()
+        tot0 = (P0 + A0).sum(axis=(0, 1, 2))
+        done, conv, v = sim.mp_step(100)
+        P, A = sim.mp_download()
+        tot = (P + A).sum(axis=(0, 1, 2))
+        assert np.allclose(tot, tot0, rtol=0, atol=1e-13 * np.abs(P0).sum())   # sum(P + Pads) conserved
+        assert (P[nat == 1] == 0).all() and (A[itf_not(nat)] == 0).all()
+        assert np.isfinite(v).all()
+
+
+def itf_not(nat):
+    itf = O.detect_interfacial(nat)
+    return ~((itf == 1) & (nat == 0))
