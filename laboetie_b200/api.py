@@ -39,7 +39,8 @@ class LbgError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "liblaboetie_gpu.so")
+    # LBG_LIB lets a tuning run point at an alternative build of the same library
+    return os.environ.get("LBG_LIB") or os.path.join(_HERE, "lib", "liblaboetie_gpu.so")
 
 
 def load_library():

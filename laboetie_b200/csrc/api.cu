@@ -113,6 +113,7 @@ struct lbg_handle_s {
 
   d3q19::Consts k{};
   int grid_lb = 148, grid_mp = 148;
+  int lb_minb = 2;  // register-allocation variant of the LB step kernel (see lb_kernels.cu)
   int64_t n_fluid = 0, n_if_fluid = 0;  // own planes
 
   Phase phase = PH_CREATED;
@@ -250,8 +251,10 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   if (!out || !nature_halo || lx < 1 || ly < 1 || lz_global < 1 || nzl < 1 || k0 < 0 || k0 + nzl > lz_global)
     return fail(nullptr, LBG_ERR_INVALID_ARG, "lbg_create: invalid argument");
   const long long plane = (long long)lx * ly;
-  const long long nalloc = plane * (nzl + 2);
-  if (nalloc > (long long)INT_MAX - 8) return fail(nullptr, LBG_ERR_INVALID_ARG, "lbg_create: slab too large for 32-bit node index");
+  // stride of every per-node array: padded to 32 elements so that each array starts on a 256-byte
+  // boundary and 32-byte sectors hold the same 4 nodes in every array
+  const long long nalloc = (plane * (nzl + 2) + 31) / 32 * 32;
+  if (nalloc > (long long)INT_MAX - 64) return fail(nullptr, LBG_ERR_INVALID_ARG, "lbg_create: slab too large for 32-bit node index");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
     return fail(nullptr, LBG_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
@@ -292,7 +295,6 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   CKB(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
   CKB(cudaEventCreate(&h->ev_t0));
   CKB(cudaEventCreate(&h->ev_t1));
-  h->grid_lb = occupancy_grid_lb(h->sm_count);
   h->grid_mp = occupancy_grid_mp(h->sm_count);
   const size_t nb = (size_t)nalloc * sizeof(double);
   CKB(cudaMalloc(&h->mask, (size_t)nalloc * sizeof(uint32_t)));
@@ -331,6 +333,10 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   CKB(cudaGetLastError());
   h->n_fluid = (int64_t)cnt[0];
   h->n_if_fluid = (int64_t)cnt[1];
+  // mostly-fluid lattices run the 3-blocks-per-SM variant, porous ones the 2-blocks one (measured, profiles/)
+  if (const char* e = std::getenv("LBG_LB_MINB")) h->lb_minb = std::atoi(e) >= 3 ? 3 : 2;
+  else h->lb_minb = (10 * h->n_fluid >= 9 * h->nown) ? 3 : 2;
+  h->grid_lb = occupancy_grid_lb(h->sm_count, h->lb_minb);
 #undef CKB
   *out = h;
   return LBG_OK;
@@ -416,22 +422,22 @@ int enqueue_lb_kernel(lbg_handle h, int fin, double tau, const ForceSel& fs, int
   if (h->nranks == 1) {
     a.g_begin = own_begin(h);
     a.g_end = own_end(h);
-    h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->grid_lb, h->st);
+    h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->lb_minb, h->grid_lb, h->st);
   } else {
     // boundary planes first, so their populations can travel while the interior runs
     a.g_begin = g.plane;
     a.g_end = 2LL * g.plane;
-    h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->grid_lb, h->st);
+    h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->lb_minb, h->grid_lb, h->st);
     if (g.nzl > 1) {
       a.g_begin = (long long)g.plane * g.nzl;
       a.g_end = (long long)g.plane * (g.nzl + 1);
-      h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->grid_lb, h->st);
+      h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->lb_minb, h->grid_lb, h->st);
     }
     RET(halo_exchange(h, h->f[1 - fin], UP_L, 5, DOWN_L, 5));
     if (g.nzl > 2) {
       a.g_begin = 2LL * g.plane;
       a.g_end = (long long)g.plane * g.nzl;
-      h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->grid_lb, h->st);
+      h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->lb_minb, h->grid_lb, h->st);
     }
     if (fl.check) {
       // global max of l2err, and the negative-population flag, before the next step looks at them
@@ -1097,21 +1103,20 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
       a.lim = lim;
       a.ctrl = h->ctrl;
       RET(wait_halo(h));
-      auto launch = [&](long long b, long long e, int accumulate) {
-        a.g_begin = b;
-        a.g_end = e;
+      auto launch = [&](int pb, int pe, int accumulate) {
+        a.p_begin = pb;
+        a.p_end = pe;
         a.accumulate = accumulate;
-        const long long nblk = (e - b + BLOCK - 1) / BLOCK;
-        h->launches += launch_mp_step(a, (int)(nblk < h->grid_mp ? nblk : h->grid_mp), h->st);
+        h->launches += launch_mp_step(a, h->grid_mp, h->st);
       };
       if (h->nranks == 1) {
-        launch(own_begin(h), own_end(h), 0);
+        launch(1, g.nzl + 1, 0);
       } else {
         const int all3[3] = {0, 1, 2};
-        launch(g.plane, 2LL * g.plane, 0);
-        if (g.nzl > 1) launch((long long)g.plane * g.nzl, (long long)g.plane * (g.nzl + 1), 1);
+        launch(1, 2, 0);
+        if (g.nzl > 1) launch(g.nzl, g.nzl + 1, 1);
         RET(halo_exchange(h, h->P[1 - pc], all3, 3, all3, 3));
-        if (g.nzl > 2) launch(2LL * g.plane, (long long)g.plane * g.nzl, 1);
+        if (g.nzl > 2) launch(2, g.nzl, 1);
         RET(wait_halo(h));
         RET(allreduce(h, h->vacf_slots + 3 * i, 3, ncclDouble, ncclSum));
       }

@@ -151,6 +151,15 @@ __device__ __forceinline__ void collide(double (&n)[NV], const Consts& k, double
   });
 }
 
+// True when the 32-byte sector (4 consecutive nodes, all arrays are 256-byte aligned and nalloc is a
+// multiple of 32) that holds node g contains a node with `bit` set.  Threads of such a sector all
+// store (zeros on solid nodes, which is what those nodes hold anyway): a fully written sector needs no
+// read-fill from HBM, a partially written one costs a DRAM read on top of the write.
+__device__ __forceinline__ bool sector_has(const uint32_t* __restrict__ mask, int g, uint32_t bit) {
+  const uint4 mm = __ldg(reinterpret_cast<const uint4*>(mask + (g & ~3)));
+  return ((mm.x | mm.y | mm.z | mm.w) & bit) != 0;
+}
+
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -158,8 +167,11 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 // ---------------------------------------------------------------------------
-template <bool TAU1, int FMODE, bool CHECK, bool WRITEJ>
-__global__ void __launch_bounds__(BLOCK) lb_step_kernel(const __grid_constant__ LBArgs a) {
+// MINB = resident blocks per SM the register allocation aims at: 3 (80 registers) keeps more loads in
+// flight on mostly-fluid lattices, 2 (124 registers, no spills) is faster on porous ones, where solid
+// lanes idle and instruction issue, not memory latency, is the co-limiter.
+template <bool TAU1, int FMODE, bool CHECK, bool WRITEJ, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_constant__ LBArgs a) {
   __shared__ int s_stop;
   __shared__ double s_red[BLOCK / 32];
   __shared__ int s_neg;
@@ -187,32 +199,38 @@ __global__ void __launch_bounds__(BLOCK) lb_step_kernel(const __grid_constant__ 
        gg += (long long)gridDim.x * BLOCK) {
     const int g = (int)gg;
     const uint32_t m = __ldg(a.mask + g);
-    if (!(m & MASK_FLUID)) continue;
-    const Nb nb = neighbours(geo, g);
+    if (!(m & MASK_FLUID) && !sector_has(a.mask, g, MASK_FLUID)) continue;
     double n[NV];
-    pull(a.fin, nalloc, g, m, nb, n);
-    double fjx = 0, fjy = 0, fjz = 0, fcx = 0, fcy = 0, fcz = 0;
-    if constexpr (FMODE == FORCE_UNIFORM) {
-      fjx = a.fj[0]; fjy = a.fj[1]; fjz = a.fj[2];
-      fcx = a.fc[0]; fcy = a.fc[1]; fcz = a.fc[2];
-    } else if constexpr (FMODE == FORCE_FIELD) {
-      fjx = a.fj_field[g]; fjy = a.fj_field[nalloc + g]; fjz = a.fj_field[2 * nalloc + g];
-      fcx = a.fc_field[g]; fcy = a.fc_field[nalloc + g]; fcz = a.fc_field[2 * nalloc + g];
-    }
-    double rho, jx, jy, jz;
-    bool neg;
-    moments(n, fjx / 2.0, fjy / 2.0, fjz / 2.0, rho, jx, jy, jz, neg);
-    any_neg |= neg;
-    if constexpr (CHECK) {
-      const double ox = a.jold[g], oy = a.jold[nalloc + g], oz = a.jold[2 * nalloc + g];
-      dmax = fmax(dmax, fmax(fabs(jx - ox), fmax(fabs(jy - oy), fabs(jz - oz))));
+    double jx = 0.0, jy = 0.0, jz = 0.0;
+    if (m & MASK_FLUID) {
+      const Nb nb = neighbours(geo, g);
+      pull(a.fin, nalloc, g, m, nb, n);
+      double fjx = 0, fjy = 0, fjz = 0, fcx = 0, fcy = 0, fcz = 0;
+      if constexpr (FMODE == FORCE_UNIFORM) {
+        fjx = a.fj[0]; fjy = a.fj[1]; fjz = a.fj[2];
+        fcx = a.fc[0]; fcy = a.fc[1]; fcz = a.fc[2];
+      } else if constexpr (FMODE == FORCE_FIELD) {
+        fjx = a.fj_field[g]; fjy = a.fj_field[nalloc + g]; fjz = a.fj_field[2 * nalloc + g];
+        fcx = a.fc_field[g]; fcy = a.fc_field[nalloc + g]; fcz = a.fc_field[2 * nalloc + g];
+      }
+      double rho;
+      bool neg;
+      moments(n, fjx / 2.0, fjy / 2.0, fjz / 2.0, rho, jx, jy, jz, neg);
+      any_neg |= neg;
+      if constexpr (CHECK) {
+        const double ox = a.jold[g], oy = a.jold[nalloc + g], oz = a.jold[2 * nalloc + g];
+        dmax = fmax(dmax, fmax(fabs(jx - ox), fmax(fabs(jy - oy), fabs(jz - oz))));
+      }
+      collide<TAU1, FMODE != FORCE_NONE>(n, a.k, rho, jx, jy, jz, fcx, fcy, fcz, a.w1, a.w2, a.w3);
+    } else {
+      // solid node sharing a sector with a fluid node: populations and j are 0 (init_simu.f90:32-39)
+      static_for<0, NV>([&](auto Lc) { n[decltype(Lc)::value] = 0.0; });
     }
     if constexpr (WRITEJ) {
       a.jnew[g] = jx;
       a.jnew[nalloc + g] = jy;
       a.jnew[2 * nalloc + g] = jz;
     }
-    collide<TAU1, FMODE != FORCE_NONE>(n, a.k, rho, jx, jy, jz, fcx, fcy, fcz, a.w1, a.w2, a.w3);
     static_for<0, NV>([&](auto Lc) {
       constexpr int L = decltype(Lc)::value;
       a.fout[(long long)L * nalloc + g] = n[L];
@@ -460,17 +478,17 @@ int launch_profile(const ProfileArgs& a, int rows, cudaStream_t st) {
 }
 
 namespace {
-template <bool TAU1, int FMODE>
+template <bool TAU1, int FMODE, int MINB>
 void launch_step_cw(const LBArgs& a, bool check, bool writej, int grid, cudaStream_t st) {
-  if (check) lb_step_kernel<TAU1, FMODE, true, true><<<grid, BLOCK, 0, st>>>(a);
-  else if (writej) lb_step_kernel<TAU1, FMODE, false, true><<<grid, BLOCK, 0, st>>>(a);
-  else lb_step_kernel<TAU1, FMODE, false, false><<<grid, BLOCK, 0, st>>>(a);
+  if (check) lb_step_kernel<TAU1, FMODE, true, true, MINB><<<grid, BLOCK, 0, st>>>(a);
+  else if (writej) lb_step_kernel<TAU1, FMODE, false, true, MINB><<<grid, BLOCK, 0, st>>>(a);
+  else lb_step_kernel<TAU1, FMODE, false, false, MINB><<<grid, BLOCK, 0, st>>>(a);
 }
-template <bool TAU1>
+template <bool TAU1, int MINB>
 void launch_step_f(const LBArgs& a, int fmode, bool check, bool writej, int grid, cudaStream_t st) {
-  if (fmode == FORCE_NONE) launch_step_cw<TAU1, FORCE_NONE>(a, check, writej, grid, st);
-  else if (fmode == FORCE_UNIFORM) launch_step_cw<TAU1, FORCE_UNIFORM>(a, check, writej, grid, st);
-  else launch_step_cw<TAU1, FORCE_FIELD>(a, check, writej, grid, st);
+  if (fmode == FORCE_NONE) launch_step_cw<TAU1, FORCE_NONE, MINB>(a, check, writej, grid, st);
+  else if (fmode == FORCE_UNIFORM) launch_step_cw<TAU1, FORCE_UNIFORM, MINB>(a, check, writej, grid, st);
+  else launch_step_cw<TAU1, FORCE_FIELD, MINB>(a, check, writej, grid, st);
 }
 template <bool TAU1>
 void launch_collide_f(const CollideArgs& a, int fmode, int grid, cudaStream_t st) {
@@ -484,10 +502,16 @@ int clamp_grid(long long n, int grid) {
 }
 }  // namespace
 
-int launch_lb_step(const LBArgs& a, bool tau1, int fmode, bool check, bool writej, int grid, cudaStream_t st) {
+int launch_lb_step(const LBArgs& a, bool tau1, int fmode, bool check, bool writej, int minb, int grid,
+                   cudaStream_t st) {
   const int gr = clamp_grid(a.g_end - a.g_begin, grid);
-  if (tau1) launch_step_f<true>(a, fmode, check, writej, gr, st);
-  else launch_step_f<false>(a, fmode, check, writej, gr, st);
+  if (minb >= 3) {
+    if (tau1) launch_step_f<true, 3>(a, fmode, check, writej, gr, st);
+    else launch_step_f<false, 3>(a, fmode, check, writej, gr, st);
+  } else {
+    if (tau1) launch_step_f<true, 2>(a, fmode, check, writej, gr, st);
+    else launch_step_f<false, 2>(a, fmode, check, writej, gr, st);
+  }
   return 1;
 }
 
@@ -506,9 +530,12 @@ int launch_moments(const MomArgs& a, int fmode, int grid, cudaStream_t st) {
   return 1;
 }
 
-int occupancy_grid_lb(int sm_count) {
+int occupancy_grid_lb(int sm_count, int minb) {
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lb_step_kernel<true, FORCE_UNIFORM, true, true>, BLOCK, 0);
+  if (minb >= 3)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lb_step_kernel<true, FORCE_UNIFORM, true, true, 3>, BLOCK, 0);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lb_step_kernel<true, FORCE_UNIFORM, true, true, 2>, BLOCK, 0);
   if (per_sm < 1) per_sm = 1;
   return sm_count * per_sm;
 }

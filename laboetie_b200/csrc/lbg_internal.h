@@ -108,7 +108,7 @@ struct MPArgs {
   double* Pnext;
   const double* Anow;   // adsorbed, 3 arrays
   double* Anext;
-  long long g_begin, g_end;
+  int p_begin, p_end;   // plane range [p_begin, p_end) to process (own planes are 1..nzl)
   double ka, kd, one_minus_kd;
   int ads;
   double* partial;      // per block partial vacf (3 each)
@@ -134,7 +134,8 @@ int launch_build_mask(const Geo& g, const int8_t* nature_halo, uint32_t* mask, c
 int launch_lb_init(const Geo& g, const uint32_t* mask, double rho0, const double a0[3], double* f, double* mom,
                    cudaStream_t st);
 int launch_collide(const CollideArgs& a, bool tau1, int fmode, int grid, cudaStream_t st);
-int launch_lb_step(const LBArgs& a, bool tau1, int fmode, bool check, bool writej, int grid, cudaStream_t st);
+int launch_lb_step(const LBArgs& a, bool tau1, int fmode, bool check, bool writej, int minb, int grid,
+                   cudaStream_t st);
 int launch_moments(const MomArgs& a, int fmode, int grid, cudaStream_t st);
 int launch_fill_force(const Geo& g, const uint32_t* mask, const double f[3], double* field, cudaStream_t st);
 int launch_profile(const ProfileArgs& a, int rows, cudaStream_t st);
@@ -143,7 +144,7 @@ int launch_extract_flag(const Geo& g, const uint32_t* mask, uint32_t bit, int8_t
 int launch_mp_init(const MPInitArgs& a, int grid, cudaStream_t st);
 int launch_mp_step(const MPArgs& a, int grid, cudaStream_t st);
 int launch_soa_to_aos3(const Geo& g, const double* soa, double* aos_own, cudaStream_t st);
-int occupancy_grid_lb(int sm_count);
+int occupancy_grid_lb(int sm_count, int minb);
 int occupancy_grid_mp(int sm_count);
 
 }  // namespace lbg

@@ -181,8 +181,36 @@ __global__ void __launch_bounds__(BLOCK) mp_init_kernel(const __grid_constant__ 
   }
 }
 
+// Tile order.  A tile is BLOCK consecutive nodes of one plane.  Tiles are walked strip by strip:
+// within a strip of STRIP tiles of the plane's linear order, all planes are visited before moving to
+// the next strip.  The three time-level-"now" planes a tile gathers from (z-1, z, z+1) and its y+-1
+// rows were then touched a few thousand tiles ago at most, so they are still in L2 (126 MB) and
+// Propagated_Quantity is read from HBM once per step instead of three times.
+constexpr int STRIP = 256;
+
+__device__ __forceinline__ bool tile_to_node(const Geo& geo, int tile, int p_begin, int np, int chunks_per_plane,
+                                             int& g) {
+  const int per_strip = STRIP * np;
+  const int strip = tile / per_strip;
+  const int rem = tile - strip * per_strip;
+  const int c0 = strip * STRIP;
+  const int cs = min(STRIP, chunks_per_plane - c0);
+  const int p = rem / cs;
+  const int c = rem - p * cs;
+  const int in_plane = (c0 + c) * BLOCK + threadIdx.x;
+  g = (p_begin + p) * geo.plane + in_plane;
+  return in_plane < geo.plane;
+}
+
 // module_moment_propagation.f90:207-253 (one propagate call), see the header comment.
-__global__ void __launch_bounds__(BLOCK) mp_step_kernel(const __grid_constant__ MPArgs a) {
+// Branch-free per node: the 18 link probabilities, the remaining fraction, u* and the node's own
+// P are streamed in first (25 independent loads in flight), then the 18 neighbour gathers are
+// issued without conditions -- a solid neighbour is replaced by the node itself and its q is 0
+// (mp_init stores 0 there), so it adds exactly 0.
+#ifndef LBG_MP_MINB
+#define LBG_MP_MINB 2
+#endif
+__global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __grid_constant__ MPArgs a) {
   __shared__ double sh[3][BLOCK / 32];
   __shared__ int s_flag;
   if (threadIdx.x == 0) {
@@ -203,41 +231,72 @@ __global__ void __launch_bounds__(BLOCK) mp_step_kernel(const __grid_constant__ 
 
   const Geo& geo = a.geo;
   const long long nalloc = geo.nalloc;
+  const int np = a.p_end - a.p_begin;
+  const int chunks = (geo.plane + BLOCK - 1) / BLOCK;
+  const int ntiles = chunks * np;
+  const uint32_t ADS = a.ads ? MASK_INTERFACIAL : 0u;  // adsorbing node <=> fluid && interfacial && ads
   double vx = 0, vy = 0, vz = 0;
-  for (long long gg = a.g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; gg < a.g_end;
-       gg += (long long)gridDim.x * BLOCK) {
-    const int g = (int)gg;
-    const uint32_t m = __ldg(a.mask + g);
-    if (!(m & MASK_FLUID)) continue;
-    const Nb nb = neighbours(geo, g);
-    double ax = 0.0, ay = 0.0, az = 0.0;  // Propagated_Quantity(:,r,next) is always 0 on entry
-    static_for<1, NV>([&](auto Lc) {
-      constexpr int L = decltype(Lc)::value;
-      if ((m >> L) & 1u) {
-        const int gp = g + offset_plus<L>(nb);
-        const double q = a.q[(long long)(L - 1) * nalloc + g];
-        ax = ax + a.Pnow[gp] * q;
-        ay = ay + a.Pnow[nalloc + gp] * q;
-        az = az + a.Pnow[2 * nalloc + gp] * q;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int g;
+    if (!tile_to_node(geo, tile, a.p_begin, np, chunks, g)) continue;
+    const uint4 mm = __ldg(reinterpret_cast<const uint4*>(a.mask + (g & ~3)));
+    const int sub = g & 3;
+    const uint32_t m = sub == 0 ? mm.x : (sub == 1 ? mm.y : (sub == 2 ? mm.z : mm.w));
+    if (!((mm.x | mm.y | mm.z | mm.w) & MASK_FLUID)) continue;  // nothing to write in this 32-byte sector
+    const bool fluid = m & MASK_FLUID;
+    const bool adsorbing = fluid && (m & ADS);
+    // does any fluid node of the sector adsorb?  (then the whole sector of the adsorbed field is written)
+    const bool sector_ads = ADS && (((mm.x & MASK_FLUID) && (mm.x & ADS)) || ((mm.y & MASK_FLUID) && (mm.y & ADS)) ||
+                                    ((mm.z & MASK_FLUID) && (mm.z & ADS)) || ((mm.w & MASK_FLUID) && (mm.w & ADS)));
+    double nx = 0.0, ny = 0.0, nz = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
+    if (fluid) {
+      double q[NV - 1];
+      static_for<1, NV>([&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        q[L - 1] = __ldcs(a.q + (long long)(L - 1) * nalloc + g);
+      });
+      const double frac = __ldcs(a.s + g);
+      const double usx = __ldcs(a.s + nalloc + g), usy = __ldcs(a.s + 2 * nalloc + g), usz = __ldcs(a.s + 3 * nalloc + g);
+      const double px = a.Pnow[g], py = a.Pnow[nalloc + g], pz = a.Pnow[2 * nalloc + g];
+      double sx = 0.0, sy = 0.0, sz = 0.0;
+      if (adsorbing) {
+        sx = a.Anow[g];
+        sy = a.Anow[nalloc + g];
+        sz = a.Anow[2 * nalloc + g];
       }
-    });
-    const double frac = a.s[g];
-    const double px = a.Pnow[g], py = a.Pnow[nalloc + g], pz = a.Pnow[2 * nalloc + g];
-    vx += px * a.s[nalloc + g];  // vacf(:,now) += P(:,r,now)*u_star   (:232)
-    vy += py * a.s[2 * nalloc + g];
-    vz += pz * a.s[3 * nalloc + g];
-    if (!(a.ads && (m & MASK_INTERFACIAL))) {  // :235-238
-      a.Pnext[g] = ax + frac * px;
-      a.Pnext[nalloc + g] = ay + frac * py;
-      a.Pnext[2 * nalloc + g] = az + frac * pz;
-    } else {  // :239-247
-      const double sx = a.Anow[g], sy = a.Anow[nalloc + g], sz = a.Anow[2 * nalloc + g];
-      a.Pnext[g] = (ax + frac * px) + sx * a.kd;
-      a.Pnext[nalloc + g] = (ay + frac * py) + sy * a.kd;
-      a.Pnext[2 * nalloc + g] = (az + frac * pz) + sz * a.kd;
-      a.Anext[g] = sx * a.one_minus_kd + px * a.ka;
-      a.Anext[nalloc + g] = sy * a.one_minus_kd + py * a.ka;
-      a.Anext[2 * nalloc + g] = sz * a.one_minus_kd + pz * a.ka;
+      const Nb nb = neighbours(geo, g);
+      double ax = 0.0, ay = 0.0, az = 0.0;  // Propagated_Quantity(:,r,next) is always 0 on entry
+      static_for<1, NV>([&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        const int gp = ((m >> L) & 1u) ? g + offset_plus<L>(nb) : g;
+        ax = ax + a.Pnow[gp] * q[L - 1];
+        ay = ay + a.Pnow[nalloc + gp] * q[L - 1];
+        az = az + a.Pnow[2 * nalloc + gp] * q[L - 1];
+      });
+      vx += px * usx;  // vacf(:,now) += P(:,r,now)*u_star   (:232)
+      vy += py * usy;
+      vz += pz * usz;
+      if (!adsorbing) {  // :235-238
+        nx = ax + frac * px;
+        ny = ay + frac * py;
+        nz = az + frac * pz;
+      } else {  // :239-247
+        nx = (ax + frac * px) + sx * a.kd;
+        ny = (ay + frac * py) + sy * a.kd;
+        nz = (az + frac * pz) + sz * a.kd;
+        bx = sx * a.one_minus_kd + px * a.ka;
+        by = sy * a.one_minus_kd + py * a.ka;
+        bz = sz * a.one_minus_kd + pz * a.ka;
+      }
+    }
+    // whole sectors are written: solid nodes hold 0, non-adsorbing nodes hold 0 in the adsorbed field
+    __stcs(a.Pnext + g, nx);
+    __stcs(a.Pnext + nalloc + g, ny);
+    __stcs(a.Pnext + 2 * nalloc + g, nz);
+    if (sector_ads) {
+      __stcs(a.Anext + g, bx);
+      __stcs(a.Anext + nalloc + g, by);
+      __stcs(a.Anext + 2 * nalloc + g, bz);
     }
   }
   // vacf: block partials, then the last block to finish adds them in block order
@@ -296,7 +355,8 @@ int launch_mp_init(const MPInitArgs& a, int grid, cudaStream_t st) {
 }
 
 int launch_mp_step(const MPArgs& a, int grid, cudaStream_t st) {
-  mp_step_kernel<<<grid, BLOCK, 0, st>>>(a);
+  const long long ntiles = (long long)((a.geo.plane + BLOCK - 1) / BLOCK) * (a.p_end - a.p_begin);
+  mp_step_kernel<<<(int)(ntiles < grid ? ntiles : grid), BLOCK, 0, st>>>(a);
   return 1;
 }
 

