@@ -344,7 +344,7 @@ def test_full_size_config2_properties():
         assert abs(n.sum() - nf) <= 1e-12 * nf                  # mass conservation
         # translation invariance in x and y of the slit: every (x,y) column is identical
         assert np.array_equal(jx, np.broadcast_to(jx[:, :1, :1], jx.shape))
-        assert np.abs(jy).max() < 1e-15 and np.abs(jz).max() < 1e-15   # cancel up to rounding of the l-ordered sum
+        assert np.abs(jy).max() < 1e-13 and np.abs(jz).max() < 1e-13   # cancel up to rounding of the l-ordered sum
         # momentum balance: d/dt sum(jx) -> 0 as the Poiseuille profile builds; sign and symmetry in z
         prof = sim.lb_profiles(2)[:, 0]
         assert (prof[1:-1] > 0).all() and prof[0] == 0 and prof[-1] == 0
