@@ -114,6 +114,7 @@ struct lbg_handle_s {
   d3q19::Consts k{};
   int grid_lb = 148, grid_mp = 148;
   int lb_minb = 2;  // register-allocation variant of the LB step kernel (see lb_kernels.cu)
+  int mp_variant = 0;  // 1 = bulk-async (TMA) pipelined propagate kernel, 0 = plain kernel (any lattice)
   int64_t n_fluid = 0, n_if_fluid = 0;  // own planes
 
   Phase phase = PH_CREATED;
@@ -295,7 +296,10 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   CKB(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
   CKB(cudaEventCreate(&h->ev_t0));
   CKB(cudaEventCreate(&h->ev_t1));
-  h->grid_mp = occupancy_grid_mp(h->sm_count);
+  // the bulk-async kernel needs 16-byte aligned runs: plane % 4 == 0 (LBG_MP_TMA=0 forces the plain kernel)
+  h->mp_variant = 0;  // measured slower than the plain kernel on every workload so far (profiles/): opt-in
+  if (const char* e = std::getenv("LBG_MP_TMA")) h->mp_variant = (std::atoi(e) != 0 && plane % 4 == 0) ? 1 : 0;
+  h->grid_mp = occupancy_grid_mp(h->sm_count, h->mp_variant);
   const size_t nb = (size_t)nalloc * sizeof(double);
   CKB(cudaMalloc(&h->mask, (size_t)nalloc * sizeof(uint32_t)));
   CKB(cudaMalloc(&h->f[0], 19 * nb));
@@ -333,9 +337,10 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   CKB(cudaGetLastError());
   h->n_fluid = (int64_t)cnt[0];
   h->n_if_fluid = (int64_t)cnt[1];
-  // mostly-fluid lattices run the 3-blocks-per-SM variant, porous ones the 2-blocks one (measured, profiles/)
+  // small, mostly-fluid slabs (latency / tail dominated) run the 3-blocks-per-SM variant, everything else
+  // the 2-blocks one (measured, profiles/variants_r1f.txt)
   if (const char* e = std::getenv("LBG_LB_MINB")) h->lb_minb = std::atoi(e) >= 3 ? 3 : 2;
-  else h->lb_minb = (10 * h->n_fluid >= 9 * h->nown) ? 3 : 2;
+  else h->lb_minb = (10 * h->n_fluid >= 9 * h->nown && h->nown < (8LL << 20)) ? 3 : 2;
   h->grid_lb = occupancy_grid_lb(h->sm_count, h->lb_minb);
 #undef CKB
   *out = h;
@@ -1107,7 +1112,7 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
         a.p_begin = pb;
         a.p_end = pe;
         a.accumulate = accumulate;
-        h->launches += launch_mp_step(a, h->grid_mp, h->st);
+        h->launches += launch_mp_step(a, h->mp_variant, h->grid_mp, h->st);
       };
       if (h->nranks == 1) {
         launch(1, g.nzl + 1, 0);

@@ -20,6 +20,13 @@
 
 #include "lbg_internal.h"
 
+#ifndef LBG_PREFETCH_MASK
+#define LBG_PREFETCH_MASK 1
+#endif
+#ifndef LBG_BLOCKED
+#define LBG_BLOCKED 0
+#endif
+
 namespace lbg {
 using namespace d3q19;
 
@@ -155,9 +162,18 @@ __device__ __forceinline__ void collide(double (&n)[NV], const Consts& k, double
 // multiple of 32) that holds node g contains a node with `bit` set.  Threads of such a sector all
 // store (zeros on solid nodes, which is what those nodes hold anyway): a fully written sector needs no
 // read-fill from HBM, a partially written one costs a DRAM read on top of the write.
+#ifndef LBG_FILL
+#define LBG_FILL 4  // nodes per fill group: 4 = one 32-byte sector
+#endif
 __device__ __forceinline__ bool sector_has(const uint32_t* __restrict__ mask, int g, uint32_t bit) {
-  const uint4 mm = __ldg(reinterpret_cast<const uint4*>(mask + (g & ~3)));
-  return ((mm.x | mm.y | mm.z | mm.w) & bit) != 0;
+  const uint4* p = reinterpret_cast<const uint4*>(mask + (g & ~(LBG_FILL - 1)));
+  uint32_t any = 0;
+#pragma unroll
+  for (int i = 0; i < LBG_FILL / 4; ++i) {
+    const uint4 mm = __ldg(p + i);
+    any |= mm.x | mm.y | mm.z | mm.w;
+  }
+  return (any & bit) != 0;
 }
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -195,10 +211,35 @@ __global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_const
   const long long nalloc = geo.nalloc;
   double dmax = 0.0;
   bool any_neg = false;
-  for (long long gg = a.g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; gg < a.g_end;
-       gg += (long long)gridDim.x * BLOCK) {
+  // tiles of BLOCK consecutive nodes; the mask word of the next tile is fetched one iteration ahead so
+  // that its DRAM latency does not sit in front of the 22 dependent population loads
+  const int ntiles = (int)((a.g_end - a.g_begin + BLOCK - 1) / BLOCK);
+#if LBG_BLOCKED
+  const int tpb = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int t_first = blockIdx.x * tpb, t_last = min(ntiles, t_first + tpb), t_step = 1;
+#else
+  const int t_first = blockIdx.x, t_last = ntiles, t_step = gridDim.x;
+#endif
+  auto node_of = [&](int tile) { return a.g_begin + (long long)tile * BLOCK + threadIdx.x; };
+#if LBG_PREFETCH_MASK
+  uint32_t m_next = 0;
+  if (t_first < t_last && node_of(t_first) < a.g_end) m_next = __ldg(a.mask + node_of(t_first));
+#endif
+  for (int tile = t_first; tile < t_last; tile += t_step) {
+    const long long gg = node_of(tile);
+#if LBG_PREFETCH_MASK
+    const uint32_t m = m_next;
+    {
+      const int tn = tile + t_step;
+      m_next = (tn < t_last && node_of(tn) < a.g_end) ? __ldg(a.mask + node_of(tn)) : 0u;
+    }
+    if (gg >= a.g_end) continue;
+    const int g = (int)gg;
+#else
+    if (gg >= a.g_end) continue;
     const int g = (int)gg;
     const uint32_t m = __ldg(a.mask + g);
+#endif
     if (!(m & MASK_FLUID) && !sector_has(a.mask, g, MASK_FLUID)) continue;
     double n[NV];
     double jx = 0.0, jy = 0.0, jz = 0.0;

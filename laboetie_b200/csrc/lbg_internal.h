@@ -142,9 +142,9 @@ int launch_profile(const ProfileArgs& a, int rows, cudaStream_t st);
 int launch_count_flags(const Geo& g, const uint32_t* mask, unsigned long long* counts2, cudaStream_t st);
 int launch_extract_flag(const Geo& g, const uint32_t* mask, uint32_t bit, int8_t* out_own, cudaStream_t st);
 int launch_mp_init(const MPInitArgs& a, int grid, cudaStream_t st);
-int launch_mp_step(const MPArgs& a, int grid, cudaStream_t st);
+int launch_mp_step(const MPArgs& a, int variant, int grid, cudaStream_t st);
 int launch_soa_to_aos3(const Geo& g, const double* soa, double* aos_own, cudaStream_t st);
 int occupancy_grid_lb(int sm_count, int minb);
-int occupancy_grid_mp(int sm_count);
+int occupancy_grid_mp(int sm_count, int variant);
 
 }  // namespace lbg

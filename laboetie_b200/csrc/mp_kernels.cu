@@ -330,6 +330,223 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bulk-async (TMA) pipelined variant of the propagate step.
+//
+// The per-node operands that are streamed exactly once per step -- 18 link probabilities, the
+// remaining fraction, u*, the node's own P and its mask word: 204 of the ~230 bytes a fluid node
+// moves -- are contiguous runs of BLOCK elements per array.  One elected thread copies them
+// global -> shared with cp.async.bulk (UBLKCP), completion counted on an mbarrier, one tile ahead
+// of the tile the CTA is working on (2 stages x 51 KB, 2 CTAs per SM).  The memory pipeline is then
+// kept full by ~100 KB of copies in flight per SM, independent of registers and occupancy, and the
+// threads only issue the 54 neighbour gathers of P (served by L1/L2 thanks to the strip order).
+// Arithmetic is unchanged, so results are bit-identical to mp_step_kernel.
+// Needs plane % 4 == 0 (16-byte alignment of every run); other lattices use mp_step_kernel.
+constexpr int MP_STAGES = 2;
+constexpr int MP_STAGE_DOUBLES = 25 * BLOCK;                                   // q[18], s[4], P[3]
+constexpr int MP_STAGE_BYTES = MP_STAGE_DOUBLES * 8 + BLOCK * 4;               // + mask
+constexpr int MP_SMEM_BYTES = MP_STAGES * MP_STAGE_BYTES + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LBG_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra LBG_DONE;\n\t"
+      "bra LBG_WAIT;\n\t"
+      "LBG_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// first node and length of a tile (uniform over the CTA)
+__device__ __forceinline__ void tile_span(const Geo& geo, int tile, int p_begin, int np, int chunks_per_plane, int& g0,
+                                          int& len) {
+  const int per_strip = STRIP * np;
+  const int strip = tile / per_strip;
+  const int rem = tile - strip * per_strip;
+  const int c0 = strip * STRIP;
+  const int cs = min(STRIP, chunks_per_plane - c0);
+  const int p = rem / cs;
+  const int c = rem - p * cs;
+  const int in_plane = (c0 + c) * BLOCK;
+  g0 = (p_begin + p) * geo.plane + in_plane;
+  len = min(BLOCK, geo.plane - in_plane);
+}
+
+__global__ void __launch_bounds__(BLOCK, 2) mp_step_tma_kernel(const __grid_constant__ MPArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double sh[3][BLOCK / 32];
+  __shared__ int s_flag;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // MP_STAGES barriers in the first 64 bytes
+  unsigned char* stage0 = smem_raw + 64;
+  if (threadIdx.x == 0) {
+    int stop = *(volatile int*)&a.ctrl->stop;
+    if (!stop && a.check_prev) {
+      const volatile double* v = a.vacf_slots + 3 * (a.batch_idx - 1);
+      const double ax = fabs(v[0]), ay = fabs(v[1]), az = fabs(v[2]);
+      if (ax < a.lim && ay < a.lim && az < a.lim && ax < 1.e-12 && ay < 1.e-12 && az < 1.e-12) {  // :284
+        a.ctrl->stop = 1;
+        a.ctrl->stop_idx = a.batch_idx;
+        stop = 1;
+      }
+    }
+    s_flag = stop;
+    for (int st = 0; st < MP_STAGES; ++st) mbar_init(&full[st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (s_flag) return;
+
+  const Geo& geo = a.geo;
+  const long long nalloc = geo.nalloc;
+  const int np = a.p_end - a.p_begin;
+  const int chunks = (geo.plane + BLOCK - 1) / BLOCK;
+  const int ntiles = chunks * np;
+  const uint32_t ADS = a.ads ? MASK_INTERFACIAL : 0u;
+
+  auto issue = [&](int tile, int st) {  // one thread
+    int g0, len;
+    tile_span(geo, tile, a.p_begin, np, chunks, g0, len);
+    double* sd = reinterpret_cast<double*>(stage0 + (size_t)st * MP_STAGE_BYTES);
+    uint32_t* sm = reinterpret_cast<uint32_t*>(sd + MP_STAGE_DOUBLES);
+    mbar_expect_tx(&full[st], (uint32_t)len * (25 * 8 + 4));
+#pragma unroll 1
+    for (int i = 0; i < 18; ++i) bulk_g2s(sd + i * BLOCK, a.q + (long long)i * nalloc + g0, len * 8, &full[st]);
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) bulk_g2s(sd + (18 + i) * BLOCK, a.s + (long long)i * nalloc + g0, len * 8, &full[st]);
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) bulk_g2s(sd + (22 + i) * BLOCK, a.Pnow + (long long)i * nalloc + g0, len * 8, &full[st]);
+    bulk_g2s(sm, a.mask + g0, len * 4, &full[st]);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < MP_STAGES; ++st) {
+      const int tile = blockIdx.x + st * gridDim.x;
+      if (tile < ntiles) issue(tile, st);
+    }
+  }
+
+  double vx = 0, vy = 0, vz = 0;
+  int k = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+    const int st = k % MP_STAGES;
+    const uint32_t parity = (k / MP_STAGES) & 1;
+    int g0, len;
+    tile_span(geo, tile, a.p_begin, np, chunks, g0, len);
+    const double* sd = reinterpret_cast<const double*>(stage0 + (size_t)st * MP_STAGE_BYTES);
+    const uint32_t* sm = reinterpret_cast<const uint32_t*>(sd + MP_STAGE_DOUBLES);
+    mbar_wait(&full[st], parity);
+    const int tid = threadIdx.x;
+    if (tid < len) {
+      const int g = g0 + tid;
+      const uint4 mm = *reinterpret_cast<const uint4*>(sm + (tid & ~3));
+      const uint32_t m = sm[tid];
+      if ((mm.x | mm.y | mm.z | mm.w) & MASK_FLUID) {
+        const bool fluid = m & MASK_FLUID;
+        const bool adsorbing = fluid && (m & ADS);
+        const bool sector_ads = ADS && (((mm.x & MASK_FLUID) && (mm.x & ADS)) || ((mm.y & MASK_FLUID) && (mm.y & ADS)) ||
+                                        ((mm.z & MASK_FLUID) && (mm.z & ADS)) || ((mm.w & MASK_FLUID) && (mm.w & ADS)));
+        double nx = 0.0, ny = 0.0, nz = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
+        if (fluid) {
+          double sx = 0.0, sy = 0.0, sz = 0.0;
+          if (adsorbing) {
+            sx = a.Anow[g];
+            sy = a.Anow[nalloc + g];
+            sz = a.Anow[2 * nalloc + g];
+          }
+          const Nb nb = neighbours(geo, g);
+          double ax = 0.0, ay = 0.0, az = 0.0;  // Propagated_Quantity(:,r,next) is always 0 on entry
+          static_for<1, NV>([&](auto Lc) {
+            constexpr int L = decltype(Lc)::value;
+            const int gp = ((m >> L) & 1u) ? g + offset_plus<L>(nb) : g;
+            const double q = sd[(L - 1) * BLOCK + tid];
+            ax = ax + a.Pnow[gp] * q;
+            ay = ay + a.Pnow[nalloc + gp] * q;
+            az = az + a.Pnow[2 * nalloc + gp] * q;
+          });
+          const double frac = sd[18 * BLOCK + tid];
+          const double px = sd[22 * BLOCK + tid], py = sd[23 * BLOCK + tid], pz = sd[24 * BLOCK + tid];
+          vx += px * sd[19 * BLOCK + tid];  // vacf(:,now) += P(:,r,now)*u_star   (:232)
+          vy += py * sd[20 * BLOCK + tid];
+          vz += pz * sd[21 * BLOCK + tid];
+          if (!adsorbing) {  // :235-238
+            nx = ax + frac * px;
+            ny = ay + frac * py;
+            nz = az + frac * pz;
+          } else {  // :239-247
+            nx = (ax + frac * px) + sx * a.kd;
+            ny = (ay + frac * py) + sy * a.kd;
+            nz = (az + frac * pz) + sz * a.kd;
+            bx = sx * a.one_minus_kd + px * a.ka;
+            by = sy * a.one_minus_kd + py * a.ka;
+            bz = sz * a.one_minus_kd + pz * a.ka;
+          }
+        }
+        __stcs(a.Pnext + g, nx);
+        __stcs(a.Pnext + nalloc + g, ny);
+        __stcs(a.Pnext + 2 * nalloc + g, nz);
+        if (sector_ads) {
+          __stcs(a.Anext + g, bx);
+          __stcs(a.Anext + nalloc + g, by);
+          __stcs(a.Anext + 2 * nalloc + g, bz);
+        }
+      }
+    }
+    __syncthreads();  // every thread is done with this stage: refill it with the tile MP_STAGES ahead
+    if (threadIdx.x == 0) {
+      const int next = tile + MP_STAGES * gridDim.x;
+      if (next < ntiles) issue(next, st);
+    }
+  }
+  // vacf: block partials, then the last block to finish adds them in block order
+  block_sum3(vx, vy, vz, sh);
+  if (threadIdx.x == 0) {
+    a.partial[3 * blockIdx.x + 0] = vx;
+    a.partial[3 * blockIdx.x + 1] = vy;
+    a.partial[3 * blockIdx.x + 2] = vz;
+    __threadfence();
+    const unsigned int done = atomicAdd(&a.ctrl->ticket, 1u);
+    if (done == gridDim.x - 1) {
+      __threadfence();
+      double tx = 0, ty = 0, tz = 0;
+      for (unsigned int b = 0; b < gridDim.x; ++b) {
+        tx += ((volatile double*)a.partial)[3 * b + 0];
+        ty += ((volatile double*)a.partial)[3 * b + 1];
+        tz += ((volatile double*)a.partial)[3 * b + 2];
+      }
+      double* slot = a.vacf_slots + 3 * a.batch_idx;
+      if (a.accumulate) {
+        slot[0] += tx;
+        slot[1] += ty;
+        slot[2] += tz;
+      } else {
+        slot[0] = tx;
+        slot[1] = ty;
+        slot[2] = tz;
+      }
+      a.ctrl->ticket = 0;
+    }
+  }
+}
+
 // SoA (3 arrays, stride nalloc, with halos) -> reference AoS (x:z,i,j,k) over own planes
 __global__ void __launch_bounds__(BLOCK) soa_to_aos3_kernel(Geo geo, const double* __restrict__ soa,
                                                             double* __restrict__ aos) {
@@ -354,9 +571,11 @@ int launch_mp_init(const MPInitArgs& a, int grid, cudaStream_t st) {
   return 1;
 }
 
-int launch_mp_step(const MPArgs& a, int grid, cudaStream_t st) {
+int launch_mp_step(const MPArgs& a, int variant, int grid, cudaStream_t st) {
   const long long ntiles = (long long)((a.geo.plane + BLOCK - 1) / BLOCK) * (a.p_end - a.p_begin);
-  mp_step_kernel<<<(int)(ntiles < grid ? ntiles : grid), BLOCK, 0, st>>>(a);
+  const int gr = (int)(ntiles < grid ? ntiles : grid);
+  if (variant == 1) mp_step_tma_kernel<<<gr, BLOCK, MP_SMEM_BYTES, st>>>(a);
+  else mp_step_kernel<<<gr, BLOCK, 0, st>>>(a);
   return 1;
 }
 
@@ -365,9 +584,14 @@ int launch_soa_to_aos3(const Geo& g, const double* soa, double* aos_own, cudaStr
   return 1;
 }
 
-int occupancy_grid_mp(int sm_count) {
+int occupancy_grid_mp(int sm_count, int variant) {
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp_step_kernel, BLOCK, 0);
+  if (variant == 1) {
+    cudaFuncSetAttribute(mp_step_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp_step_tma_kernel, BLOCK, MP_SMEM_BYTES);
+  } else {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp_step_kernel, BLOCK, 0);
+  }
   if (per_sm < 1) per_sm = 1;
   return sm_count * per_sm;
 }

@@ -129,6 +129,7 @@ def porous_spheres(lx, ly, lz, porosity=0.6, radius=8, seed=12345, k0=0, nz=None
 WORKLOADS = {
     # name: (builder, lx, ly, lz per GPU, f_ext, description)
     "cfg2": (slit, 64, 64, 256, (1e-6, 0.0, 0.0), "geometryLabel=1 slit 64x64x256"),
+    "slitL": (slit, 512, 512, 256, (1e-6, 0.0, 0.0), "geometryLabel=1 slit 512x512x256 (all-fluid steady-state probe)"),
     "cfg3": (bcc, 256, 256, 256, (1e-6, 0.0, 0.0), "geometryLabel=3 BCC spheres 256^3"),
     "cfg5w": (porous_spheres, 1024, 1024, 128, (1e-6, 0.0, 0.0),
               "synthetic random porous 1024x1024x(128 per GPU), spheres r=8, porosity~0.6, splitmix64 seed 12345"),

@@ -355,7 +355,7 @@ def test_full_size_config2_properties():
         done, conv, v = sim.mp_step(100)
         P, A = sim.mp_download()
         tot = (P + A).sum(axis=(0, 1, 2))
-        assert np.allclose(tot, tot0, rtol=0, atol=1e-13 * np.abs(P0).sum())   # sum(P + Pads) conserved
+        assert np.allclose(tot, tot0, rtol=0, atol=1e-11 * np.abs(P0).sum())   # sum(P + Pads) conserved up to rounding over 100 steps
         assert (P[nat == 1] == 0).all() and (A[itf_not(nat)] == 0).all()
         assert np.isfinite(v).all()
 
