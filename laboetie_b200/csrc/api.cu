@@ -339,8 +339,10 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   h->n_if_fluid = (int64_t)cnt[1];
   // small, mostly-fluid slabs (latency / tail dominated) run the 3-blocks-per-SM variant, everything else
   // the 2-blocks one (measured, profiles/variants_r1f.txt)
-  if (const char* e = std::getenv("LBG_LB_MINB")) h->lb_minb = std::atoi(e) >= 3 ? 3 : 2;
-  else h->lb_minb = (10 * h->n_fluid >= 9 * h->nown && h->nown < (8LL << 20)) ? 3 : 2;
+  // porous slabs (< 90 % fluid) run the block-compacting kernel (variant 0)
+  if (const char* e = std::getenv("LBG_LB_MINB")) h->lb_minb = std::atoi(e);
+  else if (10 * h->n_fluid < 9 * h->nown) h->lb_minb = 0;
+  else h->lb_minb = (h->nown < (8LL << 20)) ? 3 : 2;
   h->grid_lb = occupancy_grid_lb(h->sm_count, h->lb_minb);
 #undef CKB
   *out = h;

@@ -26,6 +26,11 @@
 #ifndef LBG_BLOCKED
 #define LBG_BLOCKED 0
 #endif
+// how the population loads go through the cache hierarchy: 0 = default (L1 allocating), 1 = .cg (L2 only),
+// 2 = .cs (streaming)
+#ifndef LBG_LOADMODE
+#define LBG_LOADMODE 1
+#endif
 
 namespace lbg {
 using namespace d3q19;
@@ -74,18 +79,28 @@ __device__ __forceinline__ int offset(const Nb& nb) {
   return o;
 }
 
+__device__ __forceinline__ double ld_pop(const double* p) {
+#if LBG_LOADMODE == 1
+  return __ldcg(p);
+#elif LBG_LOADMODE == 2
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
+
 // n(t)(r,·) by pull with halfway bounce-back.
 __device__ __forceinline__ void pull(const double* __restrict__ fin, long long nalloc, int g, uint32_t m, const Nb& nb,
                                      double (&n)[NV]) {
   static_for<0, NV>([&](auto Lc) {
     constexpr int L = decltype(Lc)::value;
     if constexpr (L == 0) {
-      n[0] = fin[g];
+      n[0] = ld_pop(fin + g);
     } else {
       const bool src_fluid = (m >> inv(L)) & 1u;  // r - c_L == r + c_inv(L)
       const int idx = src_fluid ? g + offset<L, -1>(nb) : g;
       const int arr = src_fluid ? L : inv(L);
-      n[L] = fin[(long long)arr * nalloc + idx];
+      n[L] = ld_pop(fin + (long long)arr * nalloc + idx);
     }
   });
 }
@@ -182,6 +197,57 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
+// One fluid node of K(t): pull, moments, convergence / negativity bookkeeping, collide, store.
+template <bool TAU1, int FMODE, bool CHECK, bool WRITEJ>
+__device__ __forceinline__ void lb_fluid_node(const LBArgs& a, int g, uint32_t m, double& dmax, bool& any_neg) {
+  const long long nalloc = a.geo.nalloc;
+  const Nb nb = neighbours(a.geo, g);
+  double n[NV];
+  pull(a.fin, nalloc, g, m, nb, n);
+  double fjx = 0, fjy = 0, fjz = 0, fcx = 0, fcy = 0, fcz = 0;
+  if constexpr (FMODE == FORCE_UNIFORM) {
+    fjx = a.fj[0]; fjy = a.fj[1]; fjz = a.fj[2];
+    fcx = a.fc[0]; fcy = a.fc[1]; fcz = a.fc[2];
+  } else if constexpr (FMODE == FORCE_FIELD) {
+    fjx = a.fj_field[g]; fjy = a.fj_field[nalloc + g]; fjz = a.fj_field[2 * nalloc + g];
+    fcx = a.fc_field[g]; fcy = a.fc_field[nalloc + g]; fcz = a.fc_field[2 * nalloc + g];
+  }
+  double rho, jx, jy, jz;
+  bool neg;
+  moments(n, fjx / 2.0, fjy / 2.0, fjz / 2.0, rho, jx, jy, jz, neg);
+  any_neg |= neg;
+  if constexpr (CHECK) {
+    const double ox = a.jold[g], oy = a.jold[nalloc + g], oz = a.jold[2 * nalloc + g];
+    dmax = fmax(dmax, fmax(fabs(jx - ox), fmax(fabs(jy - oy), fabs(jz - oz))));
+  }
+  if constexpr (WRITEJ) {
+    a.jnew[g] = jx;
+    a.jnew[nalloc + g] = jy;
+    a.jnew[2 * nalloc + g] = jz;
+  }
+  collide<TAU1, FMODE != FORCE_NONE>(n, a.k, rho, jx, jy, jz, fcx, fcy, fcz, a.w1, a.w2, a.w3);
+  static_for<0, NV>([&](auto Lc) {
+    constexpr int L = decltype(Lc)::value;
+    a.fout[(long long)L * nalloc + g] = n[L];
+  });
+}
+
+// A solid node that shares a 32-byte sector with a fluid node stores its zeros (populations and j are 0
+// on solid nodes, init_simu.f90:32-39), so the sector is written whole and needs no read-fill from HBM.
+template <bool WRITEJ>
+__device__ __forceinline__ void lb_fill_node(const LBArgs& a, int g) {
+  const long long nalloc = a.geo.nalloc;
+  if constexpr (WRITEJ) {
+    a.jnew[g] = 0.0;
+    a.jnew[nalloc + g] = 0.0;
+    a.jnew[2 * nalloc + g] = 0.0;
+  }
+  static_for<0, NV>([&](auto Lc) {
+    constexpr int L = decltype(Lc)::value;
+    a.fout[(long long)L * nalloc + g] = 0.0;
+  });
+}
+
 // ---------------------------------------------------------------------------
 // MINB = resident blocks per SM the register allocation aims at: 3 (80 registers) keeps more loads in
 // flight on mostly-fluid lattices, 2 (124 registers, no spills) is faster on porous ones, where solid
@@ -240,42 +306,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_const
     const int g = (int)gg;
     const uint32_t m = __ldg(a.mask + g);
 #endif
-    if (!(m & MASK_FLUID) && !sector_has(a.mask, g, MASK_FLUID)) continue;
-    double n[NV];
-    double jx = 0.0, jy = 0.0, jz = 0.0;
-    if (m & MASK_FLUID) {
-      const Nb nb = neighbours(geo, g);
-      pull(a.fin, nalloc, g, m, nb, n);
-      double fjx = 0, fjy = 0, fjz = 0, fcx = 0, fcy = 0, fcz = 0;
-      if constexpr (FMODE == FORCE_UNIFORM) {
-        fjx = a.fj[0]; fjy = a.fj[1]; fjz = a.fj[2];
-        fcx = a.fc[0]; fcy = a.fc[1]; fcz = a.fc[2];
-      } else if constexpr (FMODE == FORCE_FIELD) {
-        fjx = a.fj_field[g]; fjy = a.fj_field[nalloc + g]; fjz = a.fj_field[2 * nalloc + g];
-        fcx = a.fc_field[g]; fcy = a.fc_field[nalloc + g]; fcz = a.fc_field[2 * nalloc + g];
-      }
-      double rho;
-      bool neg;
-      moments(n, fjx / 2.0, fjy / 2.0, fjz / 2.0, rho, jx, jy, jz, neg);
-      any_neg |= neg;
-      if constexpr (CHECK) {
-        const double ox = a.jold[g], oy = a.jold[nalloc + g], oz = a.jold[2 * nalloc + g];
-        dmax = fmax(dmax, fmax(fabs(jx - ox), fmax(fabs(jy - oy), fabs(jz - oz))));
-      }
-      collide<TAU1, FMODE != FORCE_NONE>(n, a.k, rho, jx, jy, jz, fcx, fcy, fcz, a.w1, a.w2, a.w3);
-    } else {
-      // solid node sharing a sector with a fluid node: populations and j are 0 (init_simu.f90:32-39)
-      static_for<0, NV>([&](auto Lc) { n[decltype(Lc)::value] = 0.0; });
-    }
-    if constexpr (WRITEJ) {
-      a.jnew[g] = jx;
-      a.jnew[nalloc + g] = jy;
-      a.jnew[2 * nalloc + g] = jz;
-    }
-    static_for<0, NV>([&](auto Lc) {
-      constexpr int L = decltype(Lc)::value;
-      a.fout[(long long)L * nalloc + g] = n[L];
-    });
+    if (m & MASK_FLUID) lb_fluid_node<TAU1, FMODE, CHECK, WRITEJ>(a, g, m, dmax, any_neg);
+    else if (sector_has(a.mask, g, MASK_FLUID)) lb_fill_node<WRITEJ>(a, g);
   }
   if (any_neg) s_neg = 1;
   if constexpr (CHECK) {
@@ -289,6 +321,155 @@ __global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_const
 #pragma unroll
       for (int w = 1; w < BLOCK / 32; ++w) v = fmax(v, s_red[w]);
       // non-negative doubles order like their bit patterns
+      atomicMax(&a.l2_slots[a.batch_idx], (unsigned long long)__double_as_longlong(v));
+    }
+    if (s_neg) atomicCAS(&a.ctrl->neg_step_idx, 0, a.batch_idx + 1);
+  }
+}
+
+// Porous lattices: the same step with block-level compaction.  A block takes a super-tile of
+// CT_NODES consecutive nodes, turns its mask words into a list of fluid nodes (ballot-free prefix
+// sums over 8-node groups) and a list of fill nodes in shared memory, and then every lane works on a
+// fluid node.  Without this a warp on a 60 %-fluid lattice runs with ~19 of 32 lanes active and the
+// kernel is bound by instruction issue and exposed latency rather than by HBM.  Per-node arithmetic
+// is the shared lb_fluid_node(), so results are identical to lb_step_kernel.
+constexpr int CT_PER_THREAD = 8;
+constexpr int CT_NODES = BLOCK * CT_PER_THREAD;
+
+template <bool TAU1, int FMODE, bool CHECK, bool WRITEJ>
+__global__ void __launch_bounds__(BLOCK, 2) lb_step_compact_kernel(const __grid_constant__ LBArgs a) {
+  __shared__ int s_stop;
+  __shared__ double s_red[BLOCK / 32];
+  __shared__ int s_neg;
+  __shared__ uint32_t s_mask[CT_NODES];
+  __shared__ unsigned short s_fluid[CT_NODES];
+  __shared__ unsigned short s_fill[CT_NODES];
+  __shared__ int s_wsum[2][BLOCK / 32];
+  __shared__ int s_tot[2];
+  if (threadIdx.x == 0) {
+    int stop = *(volatile int*)&a.ctrl->stop | *(volatile int*)&a.ctrl->neg_step_idx;
+    if (!stop && a.prev_checked && a.prev_may_stop) {
+      const double prev = __longlong_as_double((long long)*(volatile unsigned long long*)&a.l2_slots[a.batch_idx - 1]);
+      if (prev <= a.target) {  // equilibration.f90:346
+        a.ctrl->stop = 1;
+        a.ctrl->stop_idx = a.batch_idx;
+        stop = 1;
+      }
+    }
+    s_stop = stop;
+    s_neg = 0;
+  }
+  __syncthreads();
+  if (s_stop) return;
+
+  double dmax = 0.0;
+  bool any_neg = false;
+  const long long g_lo = a.g_begin & ~7LL;  // super-tiles start on an 8-node boundary (uint4 mask loads)
+  const int ntiles = (int)((a.g_end - g_lo + CT_NODES - 1) / CT_NODES);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  auto load_masks = [&](int tile, uint32_t (&mk)[CT_PER_THREAD]) {
+    const long long g0 = g_lo + (long long)tile * CT_NODES + threadIdx.x * CT_PER_THREAD;
+#pragma unroll
+    for (int i = 0; i < CT_PER_THREAD; ++i) mk[i] = 0;
+    if (tile < ntiles && g0 < a.g_end) {  // nalloc is padded, so the vector loads stay inside the array
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(a.mask + g0));
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.mask + g0 + 4));
+      mk[0] = u.x; mk[1] = u.y; mk[2] = u.z; mk[3] = u.w;
+      mk[4] = v.x; mk[5] = v.y; mk[6] = v.z; mk[7] = v.w;
+#pragma unroll
+      for (int i = 0; i < CT_PER_THREAD; ++i)
+        if (g0 + i < a.g_begin || g0 + i >= a.g_end) mk[i] = 0;  // outside this launch's range
+    }
+  };
+
+  uint32_t mk[CT_PER_THREAD], mk_next[CT_PER_THREAD];
+  load_masks(blockIdx.x, mk_next);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#pragma unroll
+    for (int i = 0; i < CT_PER_THREAD; ++i) mk[i] = mk_next[i];
+    load_masks(tile + gridDim.x, mk_next);  // one super-tile ahead
+    // --- phase 1: lists of fluid nodes and of fill nodes (solid, in a sector with a fluid node)
+    int nf = 0, nz = 0;
+    const bool g0_has = ((mk[0] | mk[1] | mk[2] | mk[3]) & MASK_FLUID) != 0;
+    const bool g1_has = ((mk[4] | mk[5] | mk[6] | mk[7]) & MASK_FLUID) != 0;
+#pragma unroll
+    for (int i = 0; i < CT_PER_THREAD; ++i) {
+      const bool fl = mk[i] & MASK_FLUID;
+      nf += fl ? 1 : 0;
+      nz += (!fl && (i < 4 ? g0_has : g1_has)) ? 1 : 0;
+    }
+    // the part of the range outside [g_begin, g_end) must not be filled either
+    {
+      const long long g0 = g_lo + (long long)tile * CT_NODES + threadIdx.x * CT_PER_THREAD;
+      int nz2 = 0;
+#pragma unroll
+      for (int i = 0; i < CT_PER_THREAD; ++i) {
+        const bool fl = mk[i] & MASK_FLUID;
+        const bool inside = (g0 + i >= a.g_begin) && (g0 + i < a.g_end);
+        nz2 += (!fl && inside && (i < 4 ? g0_has : g1_has)) ? 1 : 0;
+      }
+      nz = nz2;
+    }
+    int pf = nf, pz = nz;  // inclusive warp scans
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int tf = __shfl_up_sync(0xffffffffu, pf, o), tz = __shfl_up_sync(0xffffffffu, pz, o);
+      if (lane >= o) {
+        pf += tf;
+        pz += tz;
+      }
+    }
+    if (lane == 31) {
+      s_wsum[0][warp] = pf;
+      s_wsum[1][warp] = pz;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      int acc = 0;
+      for (int w = 0; w < BLOCK / 32; ++w) {
+        const int v = s_wsum[threadIdx.x][w];
+        s_wsum[threadIdx.x][w] = acc;
+        acc += v;
+      }
+      s_tot[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    {
+      int of = s_wsum[0][warp] + pf - nf, oz = s_wsum[1][warp] + pz - nz;
+      const long long g0 = g_lo + (long long)tile * CT_NODES + threadIdx.x * CT_PER_THREAD;
+#pragma unroll
+      for (int i = 0; i < CT_PER_THREAD; ++i) {
+        const int off = threadIdx.x * CT_PER_THREAD + i;
+        s_mask[off] = mk[i];
+        const bool fl = mk[i] & MASK_FLUID;
+        const bool inside = (g0 + i >= a.g_begin) && (g0 + i < a.g_end);
+        if (fl) s_fluid[of++] = (unsigned short)off;
+        else if (inside && (i < 4 ? g0_has : g1_has)) s_fill[oz++] = (unsigned short)off;
+      }
+    }
+    __syncthreads();
+    // --- phase 2: every lane on a fluid node
+    const int tot_f = s_tot[0], tot_z = s_tot[1];
+    const long long base = g_lo + (long long)tile * CT_NODES;
+    for (int i = threadIdx.x; i < tot_f; i += BLOCK) {
+      const int off = s_fluid[i];
+      lb_fluid_node<TAU1, FMODE, CHECK, WRITEJ>(a, (int)(base + off), s_mask[off], dmax, any_neg);
+    }
+    for (int i = threadIdx.x; i < tot_z; i += BLOCK) lb_fill_node<WRITEJ>(a, (int)(base + s_fill[i]));
+    __syncthreads();  // lists are rebuilt by the next super-tile
+  }
+  if (any_neg) s_neg = 1;
+  if constexpr (CHECK) {
+    dmax = warp_max(dmax);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = dmax;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if constexpr (CHECK) {
+      double v = s_red[0];
+#pragma unroll
+      for (int w = 1; w < BLOCK / 32; ++w) v = fmax(v, s_red[w]);
       atomicMax(&a.l2_slots[a.batch_idx], (unsigned long long)__double_as_longlong(v));
     }
     if (s_neg) atomicCAS(&a.ctrl->neg_step_idx, 0, a.batch_idx + 1);
@@ -543,8 +724,30 @@ int clamp_grid(long long n, int grid) {
 }
 }  // namespace
 
+namespace {
+template <bool TAU1, int FMODE>
+void launch_compact_cw(const LBArgs& a, bool check, bool writej, int grid, cudaStream_t st) {
+  if (check) lb_step_compact_kernel<TAU1, FMODE, true, true><<<grid, BLOCK, 0, st>>>(a);
+  else if (writej) lb_step_compact_kernel<TAU1, FMODE, false, true><<<grid, BLOCK, 0, st>>>(a);
+  else lb_step_compact_kernel<TAU1, FMODE, false, false><<<grid, BLOCK, 0, st>>>(a);
+}
+template <bool TAU1>
+void launch_compact_f(const LBArgs& a, int fmode, bool check, bool writej, int grid, cudaStream_t st) {
+  if (fmode == FORCE_NONE) launch_compact_cw<TAU1, FORCE_NONE>(a, check, writej, grid, st);
+  else if (fmode == FORCE_UNIFORM) launch_compact_cw<TAU1, FORCE_UNIFORM>(a, check, writej, grid, st);
+  else launch_compact_cw<TAU1, FORCE_FIELD>(a, check, writej, grid, st);
+}
+}  // namespace
+
 int launch_lb_step(const LBArgs& a, bool tau1, int fmode, bool check, bool writej, int minb, int grid,
                    cudaStream_t st) {
+  if (minb == 0) {  // block-compacting kernel for porous lattices
+    const long long nt = (a.g_end - (a.g_begin & ~7LL) + CT_NODES - 1) / CT_NODES;
+    const int gr = (int)(nt < 1 ? 1 : (nt < grid ? nt : grid));
+    if (tau1) launch_compact_f<true>(a, fmode, check, writej, gr, st);
+    else launch_compact_f<false>(a, fmode, check, writej, gr, st);
+    return 1;
+  }
   const int gr = clamp_grid(a.g_end - a.g_begin, grid);
   if (minb >= 3) {
     if (tau1) launch_step_f<true, 3>(a, fmode, check, writej, gr, st);
@@ -573,7 +776,9 @@ int launch_moments(const MomArgs& a, int fmode, int grid, cudaStream_t st) {
 
 int occupancy_grid_lb(int sm_count, int minb) {
   int per_sm = 0;
-  if (minb >= 3)
+  if (minb == 0)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lb_step_compact_kernel<true, FORCE_UNIFORM, true, true>, BLOCK, 0);
+  else if (minb >= 3)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lb_step_kernel<true, FORCE_UNIFORM, true, true, 3>, BLOCK, 0);
   else
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lb_step_kernel<true, FORCE_UNIFORM, true, true, 2>, BLOCK, 0);

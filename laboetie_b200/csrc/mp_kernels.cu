@@ -187,6 +187,18 @@ __global__ void __launch_bounds__(BLOCK) mp_init_kernel(const __grid_constant__ 
 // rows were then touched a few thousand tiles ago at most, so they are still in L2 (126 MB) and
 // Propagated_Quantity is read from HBM once per step instead of three times.
 constexpr int STRIP = 256;
+#ifndef LBG_MP_LOADMODE
+#define LBG_MP_LOADMODE 2
+#endif
+__device__ __forceinline__ double ld_stream(const double* p) {
+#if LBG_MP_LOADMODE == 1
+  return __ldcg(p);
+#elif LBG_MP_LOADMODE == 2
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
 
 __device__ __forceinline__ bool tile_to_node(const Geo& geo, int tile, int p_begin, int np, int chunks_per_plane,
                                              int& g) {
@@ -253,10 +265,10 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
       double q[NV - 1];
       static_for<1, NV>([&](auto Lc) {
         constexpr int L = decltype(Lc)::value;
-        q[L - 1] = __ldcs(a.q + (long long)(L - 1) * nalloc + g);
+        q[L - 1] = ld_stream(a.q + (long long)(L - 1) * nalloc + g);
       });
-      const double frac = __ldcs(a.s + g);
-      const double usx = __ldcs(a.s + nalloc + g), usy = __ldcs(a.s + 2 * nalloc + g), usz = __ldcs(a.s + 3 * nalloc + g);
+      const double frac = ld_stream(a.s + g);
+      const double usx = ld_stream(a.s + nalloc + g), usy = ld_stream(a.s + 2 * nalloc + g), usz = ld_stream(a.s + 3 * nalloc + g);
       const double px = a.Pnow[g], py = a.Pnow[nalloc + g], pz = a.Pnow[2 * nalloc + g];
       double sx = 0.0, sy = 0.0, sz = 0.0;
       if (adsorbing) {
