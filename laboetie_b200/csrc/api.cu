@@ -1,19 +1,20 @@
 // api.cu -- host side of the C ABI declared in include/laboetie_gpu.h.
 //
-// One handle owns one GPU and one z-slab.  Device memory per node (fp64 SoA):
+// One handle owns one GPU and one z-slab.  Storage is fluid-compacted (lbg_internal.h): per fluid
+// node of the slab (own planes + one halo plane each side), fp64 SoA with stride nfa:
 //   f[2]   2 x 19   populations, two-lattice (source / destination of a step)
 //   mom    4        density, jx, jy, jz as the driver sees them
 //   jpp[2] 2 x 3    momentum density of the last two steps (for max|j - j_old|)
-//   mask   1 u32    fluid bit, 18 neighbour-is-fluid bits, interfacial bit
-// Phase B reuses f[0] for the 18 link probabilities and f[1] for the remaining
-// fraction / u*, both time levels of Propagated_Quantity and of the adsorbed
-// quantity (the reference drops its populations there too, drop_tracers.f90:85).
+//   gidx   1 u32    dense node index, bit 31 = interfacial
+// plus the rank structure words[] (8 bytes per 32 lattice nodes).  Phase B reuses f[0] for the 18 link
+// probabilities and f[1] for the remaining fraction / u*, both time levels of Propagated_Quantity and
+// of the adsorbed quantity (the reference drops its populations there too, drop_tracers.f90:85).
+// The driver's dense (i,j,k) arrays are scattered / gathered at the phase boundaries.
 //
-// Multi-GPU: the slab ring exchanges, per step, the 5 populations leaving each
-// z-face (ncclSend/ncclRecv straight from / into the contiguous boundary and halo
-// planes -- no packing), overlapped with the interior planes' kernel; scalars go
-// through ncclAllReduce.  NCCL is loaded with dlopen only when lbg_comm_init is
-// called, so single-GPU use has no NCCL dependency.
+// Multi-GPU: the slab ring exchanges, per step, the 5 populations leaving each z-face.  A plane's
+// fluid nodes are one contiguous fid range, so ncclSend/ncclRecv work straight on the boundary and
+// halo ranges -- no packing -- overlapped with the interior planes' kernel; scalars go through
+// ncclAllReduce.  NCCL is loaded with dlopen only when lbg_comm_init is called.
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -74,7 +75,7 @@ struct Nccl {
 struct Force {
   int mode = FORCE_NONE;  // FORCE_NONE / FORCE_UNIFORM / FORCE_FIELD
   double u[3] = {0, 0, 0};
-  double* field = nullptr;  // 3 arrays, stride nalloc (owned)
+  double* field = nullptr;  // 3 arrays, stride nfa (owned)
 };
 
 enum Phase { PH_CREATED = 0, PH_LB = 1, PH_MP = 2 };
@@ -86,7 +87,10 @@ struct lbg_handle_s {
   int sm_count = 148;
   Geo geo{};
   int lz_global = 0, k0 = 0;
-  long long nown = 0;
+  long long nown = 0;    // lattice nodes of the own planes
+  long long nf = 0;      // fluid nodes of the slab incl. halo planes
+  long long nwords = 0;
+  std::vector<long long> pstart;  // first fid of plane p, p = 0..nzl+2
   std::string err;
   long long launches = 0;
 
@@ -96,10 +100,12 @@ struct lbg_handle_s {
   cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   bool halo_pending = false;
 
-  uint32_t* mask = nullptr;
+  uint2* words = nullptr;
+  uint32_t* gidx = nullptr;
   double* f[2] = {nullptr, nullptr};
   double* mom = nullptr;
   double* jpp[2] = {nullptr, nullptr};
+  double* stage = nullptr;  // dense staging buffer for host transfers (3 * nown doubles, lazily)
   unsigned long long* l2_slots = nullptr;
   double* vacf_slots = nullptr;
   double* partial = nullptr;
@@ -114,7 +120,6 @@ struct lbg_handle_s {
   d3q19::Consts k{};
   int grid_lb = 148, grid_mp = 148;
   int lb_minb = 2;  // register-allocation variant of the LB step kernel (see lb_kernels.cu)
-  int mp_variant = 0;  // 1 = bulk-async (TMA) pipelined propagate kernel, 0 = plain kernel (any lattice)
   int64_t n_fluid = 0, n_if_fluid = 0;  // own planes
 
   Phase phase = PH_CREATED;
@@ -191,32 +196,35 @@ d3q19::Consts make_consts() {
   return k;
 }
 
-long long own_begin(const lbg_handle h) { return h->geo.plane; }
-long long own_end(const lbg_handle h) { return (long long)h->geo.plane * (h->geo.nzl + 1); }
+// fid ranges
+long long own_begin(const lbg_handle h) { return h->pstart[1]; }
+long long own_end(const lbg_handle h) { return h->pstart[h->geo.nzl + 1]; }
 
 int up_rank(const lbg_handle h) { return (h->rank + 1) % h->nranks; }
 int down_rank(const lbg_handle h) { return (h->rank + h->nranks - 1) % h->nranks; }
 
-// Exchange `narr` arrays' boundary planes with the ring neighbours.  up_list /
-// down_list name the arrays (index into base, stride nalloc) whose top own plane
-// goes to the upper neighbour's lower halo / whose bottom own plane goes to the
-// lower neighbour's upper halo.  Runs on st_comm after everything enqueued on st.
+// Exchange boundary planes with the ring neighbours.  up_list / down_list name the arrays (index into
+// base, stride nfa) whose top own plane goes to the upper neighbour's lower halo / whose bottom own
+// plane goes to the lower neighbour's upper halo.  Runs on st_comm after everything enqueued on st.
 int halo_exchange(lbg_handle h, double* base, const int* up_list, int nup, const int* down_list, int ndown) {
   if (h->nranks == 1) return LBG_OK;
   const Geo& g = h->geo;
-  const size_t cnt = (size_t)g.plane;
+  const std::vector<long long>& ps = h->pstart;
+  const int nz = g.nzl;
+  const size_t top_cnt = (size_t)(ps[nz + 1] - ps[nz]), bot_cnt = (size_t)(ps[2] - ps[1]);
+  const size_t lo_halo_cnt = (size_t)(ps[1] - ps[0]), hi_halo_cnt = (size_t)(ps[nz + 2] - ps[nz + 1]);
   CK(cudaEventRecord(h->ev_ready, h->st));
   CK(cudaStreamWaitEvent(h->st_comm, h->ev_ready, 0));
   NK(g_nccl.GroupStart());
   for (int i = 0; i < nup; ++i) {
-    double* a = base + (long long)up_list[i] * g.nalloc;
-    NK(g_nccl.Send(a + (long long)g.plane * g.nzl, cnt, ncclDouble, up_rank(h), h->comm, h->st_comm));
-    NK(g_nccl.Recv(a, cnt, ncclDouble, down_rank(h), h->comm, h->st_comm));
+    double* a = base + (long long)up_list[i] * g.nfa;
+    if (top_cnt) NK(g_nccl.Send(a + ps[nz], top_cnt, ncclDouble, up_rank(h), h->comm, h->st_comm));
+    if (lo_halo_cnt) NK(g_nccl.Recv(a + ps[0], lo_halo_cnt, ncclDouble, down_rank(h), h->comm, h->st_comm));
   }
   for (int i = 0; i < ndown; ++i) {
-    double* a = base + (long long)down_list[i] * g.nalloc;
-    NK(g_nccl.Send(a + (long long)g.plane, cnt, ncclDouble, down_rank(h), h->comm, h->st_comm));
-    NK(g_nccl.Recv(a + (long long)g.plane * (g.nzl + 1), cnt, ncclDouble, up_rank(h), h->comm, h->st_comm));
+    double* a = base + (long long)down_list[i] * g.nfa;
+    if (bot_cnt) NK(g_nccl.Send(a + ps[1], bot_cnt, ncclDouble, down_rank(h), h->comm, h->st_comm));
+    if (hi_halo_cnt) NK(g_nccl.Recv(a + ps[nz + 1], hi_halo_cnt, ncclDouble, up_rank(h), h->comm, h->st_comm));
   }
   NK(g_nccl.GroupEnd());
   CK(cudaEventRecord(h->ev_halo, h->st_comm));
@@ -235,7 +243,7 @@ int wait_halo(lbg_handle h) {
 const int UP_L[5] = {5, 11, 12, 15, 16};     // cz = +1  (reference l = 6,12,13,16,17)
 const int DOWN_L[5] = {6, 13, 14, 17, 18};   // cz = -1  (reference l = 7,14,15,18,19)
 
-// all-reduce `n` doubles in place across the ring, ordered after st, result visible to st
+// all-reduce in place across the ring, ordered after st, result visible to st after wait_halo
 int allreduce(lbg_handle h, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t op) {
   if (h->nranks == 1) return LBG_OK;
   CK(cudaEventRecord(h->ev_ready, h->st));
@@ -246,16 +254,27 @@ int allreduce(lbg_handle h, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t 
   return LBG_OK;
 }
 
+__global__ void plane_starts_kernel(Geo geo, long long ndense, long long total, long long* out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > geo.nzl + 2) return;
+  const long long g = (long long)p * geo.plane;
+  if (g >= ndense) {
+    out[p] = total;
+    return;
+  }
+  const uint2 w = geo.words[g >> 5];
+  const unsigned bit = (unsigned)(g & 31);
+  out[p] = (long long)w.y + __popc(w.x & ((1u << bit) - 1u));
+}
+
 int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nzl, const int8_t* nature_halo,
                   int device, bool zwrap) {
   lbg_handle h = nullptr;
   if (!out || !nature_halo || lx < 1 || ly < 1 || lz_global < 1 || nzl < 1 || k0 < 0 || k0 + nzl > lz_global)
     return fail(nullptr, LBG_ERR_INVALID_ARG, "lbg_create: invalid argument");
   const long long plane = (long long)lx * ly;
-  // stride of every per-node array: padded to 32 elements so that each array starts on a 256-byte
-  // boundary and 32-byte sectors hold the same 4 nodes in every array
-  const long long nalloc = (plane * (nzl + 2) + 31) / 32 * 32;
-  if (nalloc > (long long)INT_MAX - 64) return fail(nullptr, LBG_ERR_INVALID_ARG, "lbg_create: slab too large for 32-bit node index");
+  const long long ndense = plane * (nzl + 2);
+  if (ndense > (long long)INT_MAX - 64) return fail(nullptr, LBG_ERR_INVALID_ARG, "lbg_create: slab too large for 32-bit node index");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
     return fail(nullptr, LBG_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
@@ -267,7 +286,6 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   h->geo.plane = (int)plane;
   h->geo.nzl = nzl;
   h->geo.zwrap = zwrap ? 1 : 0;
-  h->geo.nalloc = nalloc;
   h->lz_global = lz_global;
   h->k0 = k0;
   h->nown = plane * nzl;
@@ -296,56 +314,78 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   CKB(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
   CKB(cudaEventCreate(&h->ev_t0));
   CKB(cudaEventCreate(&h->ev_t1));
-  // the bulk-async kernel needs 16-byte aligned runs: plane % 4 == 0 (LBG_MP_TMA=0 forces the plain kernel)
-  h->mp_variant = 0;  // measured slower than the plain kernel on every workload so far (profiles/): opt-in
-  if (const char* e = std::getenv("LBG_MP_TMA")) h->mp_variant = (std::atoi(e) != 0 && plane % 4 == 0) ? 1 : 0;
-  h->grid_mp = occupancy_grid_mp(h->sm_count, h->mp_variant);
-  const size_t nb = (size_t)nalloc * sizeof(double);
-  CKB(cudaMalloc(&h->mask, (size_t)nalloc * sizeof(uint32_t)));
-  CKB(cudaMalloc(&h->f[0], 19 * nb));
-  CKB(cudaMalloc(&h->f[1], 19 * nb));
-  CKB(cudaMalloc(&h->mom, 4 * nb));
-  CKB(cudaMalloc(&h->jpp[0], 3 * nb));
-  CKB(cudaMalloc(&h->jpp[1], 3 * nb));
+  h->grid_mp = occupancy_grid_mp(h->sm_count);
   CKB(cudaMalloc(&h->l2_slots, SLOT_CAP * sizeof(unsigned long long)));
   CKB(cudaMalloc(&h->vacf_slots, 3 * SLOT_CAP * sizeof(double)));
-  const int maxgrid = (h->grid_lb > h->grid_mp ? h->grid_lb : h->grid_mp) + 8;
-  CKB(cudaMalloc(&h->partial, 3 * (size_t)maxgrid * sizeof(double)));
   CKB(cudaMalloc(&h->ctrl, sizeof(Ctrl)));
   CKB(cudaMalloc(&h->mp_err, sizeof(int)));
   CKB(cudaMalloc(&h->counts, 2 * sizeof(unsigned long long)));
   CKB(cudaMallocHost(&h->h_l2, SLOT_CAP * sizeof(unsigned long long)));
   CKB(cudaMallocHost(&h->h_vacf, 3 * SLOT_CAP * sizeof(double)));
   CKB(cudaMallocHost(&h->h_ctrl, sizeof(Ctrl)));
-  CKB(cudaMemsetAsync(h->mask, 0, (size_t)nalloc * sizeof(uint32_t), h->st));
-  CKB(cudaMemsetAsync(h->f[0], 0, 19 * nb, h->st));
-  CKB(cudaMemsetAsync(h->f[1], 0, 19 * nb, h->st));
-  CKB(cudaMemsetAsync(h->mom, 0, 4 * nb, h->st));
-  CKB(cudaMemsetAsync(h->jpp[0], 0, 3 * nb, h->st));
-  CKB(cudaMemsetAsync(h->jpp[1], 0, 3 * nb, h->st));
   CKB(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
   CKB(cudaMemsetAsync(h->counts, 0, 2 * sizeof(unsigned long long), h->st));
-  // nature (with halo planes) is staged in f[1] and dropped once the masks exist
-  int8_t* nat_d = reinterpret_cast<int8_t*>(h->f[1]);
-  CKB(cudaMemcpyAsync(nat_d, nature_halo, (size_t)nalloc, cudaMemcpyHostToDevice, h->st));
-  h->launches += launch_build_mask(h->geo, nat_d, h->mask, h->st);
-  h->launches += launch_count_flags(h->geo, h->mask, h->counts, h->st);
-  CKB(cudaMemsetAsync(h->f[1], 0, (size_t)nalloc, h->st));
-  unsigned long long cnt[2];
-  CKB(cudaMemcpyAsync(cnt, h->counts, sizeof(cnt), cudaMemcpyDeviceToHost, h->st));
+
+  // ---- numbering: nature -> fluid bits + ranks -> plane starts -> gidx
+  h->nwords = (ndense + 31) / 32;
+  CKB(cudaMalloc(&h->words, (size_t)h->nwords * sizeof(uint2)));
+  h->geo.words = h->words;
+  int8_t* nat_d = nullptr;
+  CKB(cudaMalloc(&nat_d, (size_t)ndense));
+  CKB(cudaMemcpyAsync(nat_d, nature_halo, (size_t)ndense, cudaMemcpyHostToDevice, h->st));
+  h->launches += launch_build_bits((int)plane, nzl, nat_d, h->words, h->nwords, h->st);
+  h->launches += launch_scan_ranks(h->words, h->nwords, h->counts, h->st);
+  unsigned long long total = 0;
+  CKB(cudaMemcpyAsync(&total, h->counts, sizeof(total), cudaMemcpyDeviceToHost, h->st));
   CKB(cudaStreamSynchronize(h->st));
   CKB(cudaGetLastError());
-  h->n_fluid = (int64_t)cnt[0];
-  h->n_if_fluid = (int64_t)cnt[1];
-  // small, mostly-fluid slabs (latency / tail dominated) run the 3-blocks-per-SM variant, everything else
-  // the 2-blocks one (measured, profiles/variants_r1f.txt)
-  // porous slabs (< 90 % fluid) run the block-compacting kernel (variant 0)
-  if (const char* e = std::getenv("LBG_LB_MINB")) h->lb_minb = std::atoi(e);
-  else if (10 * h->n_fluid < 9 * h->nown) h->lb_minb = 0;
-  else h->lb_minb = (h->nown < (8LL << 20)) ? 3 : 2;
+  cudaFree(nat_d);
+  h->nf = (long long)total;
+  h->geo.nfa = (h->nf + 31) / 32 * 32;
+  if (h->geo.nfa == 0) h->geo.nfa = 32;
+  {
+    long long* d_ps = nullptr;
+    CKB(cudaMalloc(&d_ps, (size_t)(nzl + 3) * sizeof(long long)));
+    plane_starts_kernel<<<(nzl + 3 + 127) / 128, 128, 0, h->st>>>(h->geo, ndense, h->nf, d_ps);
+    h->launches += 1;
+    h->pstart.resize(nzl + 3);
+    CKB(cudaMemcpyAsync(h->pstart.data(), d_ps, (size_t)(nzl + 3) * sizeof(long long), cudaMemcpyDeviceToHost, h->st));
+    CKB(cudaStreamSynchronize(h->st));
+    cudaFree(d_ps);
+  }
+  CKB(cudaMalloc(&h->gidx, (size_t)h->geo.nfa * sizeof(uint32_t)));
+  CKB(cudaMemsetAsync(h->gidx, 0, (size_t)h->geo.nfa * sizeof(uint32_t), h->st));
+  h->geo.gidx = h->gidx;
+  h->launches += launch_build_gidx(h->geo, h->nwords, h->gidx, h->st);
+  CKB(cudaMemsetAsync(h->counts, 0, 2 * sizeof(unsigned long long), h->st));
+  h->launches += launch_count_interfacial(h->geo, own_begin(h), own_end(h), h->counts, h->st);
+  unsigned long long nif = 0;
+  CKB(cudaMemcpyAsync(&nif, h->counts, sizeof(nif), cudaMemcpyDeviceToHost, h->st));
+  CKB(cudaStreamSynchronize(h->st));
+  CKB(cudaGetLastError());
+  h->n_fluid = (int64_t)(own_end(h) - own_begin(h));
+  h->n_if_fluid = (int64_t)nif;
+
+  // ---- fields
+  const size_t nb = (size_t)h->geo.nfa * sizeof(double);
+  CKB(cudaMalloc(&h->f[0], 19 * nb));
+  CKB(cudaMalloc(&h->f[1], 19 * nb));
+  CKB(cudaMalloc(&h->mom, 4 * nb));
+  CKB(cudaMalloc(&h->jpp[0], 3 * nb));
+  CKB(cudaMalloc(&h->jpp[1], 3 * nb));
+  const int maxgrid = h->grid_mp + 8;
+  CKB(cudaMalloc(&h->partial, 3 * (size_t)maxgrid * sizeof(double)));
+  // small slabs (latency / tail dominated) run the 3-blocks-per-SM variant (profiles/variants_r1f.txt)
+  if (const char* e = std::getenv("LBG_LB_MINB")) h->lb_minb = std::atoi(e) >= 3 ? 3 : 2;
+  else h->lb_minb = (h->n_fluid < (8LL << 20)) ? 3 : 2;
   h->grid_lb = occupancy_grid_lb(h->sm_count, h->lb_minb);
 #undef CKB
   *out = h;
+  return LBG_OK;
+}
+
+int ensure_stage(lbg_handle h) {
+  if (!h->stage) CK(cudaMalloc(&h->stage, 3 * (size_t)h->nown * sizeof(double)));
   return LBG_OK;
 }
 
@@ -353,18 +393,19 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
 const Force& force_of_last_step(const lbg_handle h) { return h->prev_equals_cur ? h->fcur : h->fprev; }
 
 int ensure_field(lbg_handle h, Force& f) {
-  if (!f.field) CK(cudaMalloc(&f.field, 3 * (size_t)h->geo.nalloc * sizeof(double)));
+  if (!f.field) CK(cudaMalloc(&f.field, 3 * (size_t)h->geo.nfa * sizeof(double)));
   return LBG_OK;
 }
 
-// make `f` usable as a field (materialise a uniform force on fluid nodes)
+// make `f` usable as a field (materialise a uniform force on the fluid nodes)
 int as_field(lbg_handle h, Force& f, double** scratch, const double** out) {
   if (f.mode == FORCE_FIELD) {
     *out = f.field;
     return LBG_OK;
   }
-  if (!*scratch) CK(cudaMalloc(scratch, 3 * (size_t)h->geo.nalloc * sizeof(double)));
-  h->launches += launch_fill_force(h->geo, h->mask, f.u, *scratch, h->st);
+  if (!*scratch) CK(cudaMalloc(scratch, 3 * (size_t)h->geo.nfa * sizeof(double)));
+  const double zero[3] = {0, 0, 0};
+  h->launches += launch_fill_force(h->geo, h->nf, f.mode == FORCE_NONE ? zero : f.u, *scratch, h->st);
   *out = *scratch;
   return LBG_OK;
 }
@@ -393,7 +434,7 @@ int select_force(lbg_handle h, Force& fj, Force& fc, ForceSel* s, double** scrat
 }
 
 struct StepFlags {
-  bool check, writej, redo;
+  bool check, writej;
   int batch_idx, prev_checked, prev_may_stop;
   double target;
 };
@@ -405,7 +446,6 @@ int enqueue_lb_kernel(lbg_handle h, int fin, double tau, const ForceSel& fs, int
   a.k = h->k;
   a.fin = h->f[fin];
   a.fout = h->f[1 - fin];
-  a.mask = h->mask;
   a.w1 = 1.0 - 1.0 / tau;
   a.w2 = 1.0 / tau;
   a.w3 = 1.0 - 1.0 / (2.0 * tau);
@@ -424,28 +464,22 @@ int enqueue_lb_kernel(lbg_handle h, int fin, double tau, const ForceSel& fs, int
   a.target = fl.target;
   a.ctrl = h->ctrl;
   const bool tau1 = (tau == 1.0);
-  const Geo& g = h->geo;
+  const std::vector<long long>& ps = h->pstart;
+  const int nz = h->geo.nzl;
   RET(wait_halo(h));
-  if (h->nranks == 1) {
-    a.g_begin = own_begin(h);
-    a.g_end = own_end(h);
+  auto launch = [&](long long b, long long e) {
+    a.fid_begin = b;
+    a.fid_end = e;
     h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->lb_minb, h->grid_lb, h->st);
+  };
+  if (h->nranks == 1) {
+    launch(own_begin(h), own_end(h));
   } else {
     // boundary planes first, so their populations can travel while the interior runs
-    a.g_begin = g.plane;
-    a.g_end = 2LL * g.plane;
-    h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->lb_minb, h->grid_lb, h->st);
-    if (g.nzl > 1) {
-      a.g_begin = (long long)g.plane * g.nzl;
-      a.g_end = (long long)g.plane * (g.nzl + 1);
-      h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->lb_minb, h->grid_lb, h->st);
-    }
+    launch(ps[1], ps[2]);
+    if (nz > 1) launch(ps[nz], ps[nz + 1]);
     RET(halo_exchange(h, h->f[1 - fin], UP_L, 5, DOWN_L, 5));
-    if (g.nzl > 2) {
-      a.g_begin = 2LL * g.plane;
-      a.g_end = (long long)g.plane * g.nzl;
-      h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->lb_minb, h->grid_lb, h->st);
-    }
+    if (nz > 2) launch(ps[2], ps[nz]);
     if (fl.check) {
       // global max of l2err, and the negative-population flag, before the next step looks at them
       RET(wait_halo(h));
@@ -473,10 +507,9 @@ int ensure_collided(lbg_handle h, double tau, bool need_j) {
       a.k = h->k;
       a.fin = h->f[h->src];
       a.fout = h->f[1 - h->src];
-      a.mask = h->mask;
       a.mom = h->mom;
-      a.g_begin = own_begin(h);
-      a.g_end = own_end(h);
+      a.fid_begin = own_begin(h);
+      a.fid_end = own_end(h);
       a.w1 = 1.0 - 1.0 / tau;
       a.w2 = 1.0 / tau;
       a.w3 = 1.0 - 1.0 / (2.0 * tau);
@@ -488,8 +521,8 @@ int ensure_collided(lbg_handle h, double tau, bool need_j) {
         rc = halo_exchange(h, h->f[1 - h->src], UP_L, 5, DOWN_L, 5);
       }
       if (rc == LBG_OK && j_missing) {
-        const size_t nb = (size_t)h->geo.nalloc * sizeof(double);
-        cudaError_t e = cudaMemcpyAsync(h->jpp[h->jc], h->mom + h->geo.nalloc, 3 * nb, cudaMemcpyDeviceToDevice, h->st);
+        const size_t nb = (size_t)h->geo.nfa * sizeof(double);
+        cudaError_t e = cudaMemcpyAsync(h->jpp[h->jc], h->mom + h->geo.nfa, 3 * nb, cudaMemcpyDeviceToDevice, h->st);
         if (e != cudaSuccess) rc = fail(h, LBG_ERR_CUDA, cudaGetErrorString(e));
         h->j_valid_step = h->t;
       }
@@ -503,7 +536,6 @@ int ensure_collided(lbg_handle h, double tau, bool need_j) {
       StepFlags fl{};
       fl.check = false;
       fl.writej = j_missing;
-      fl.redo = true;
       // K(t) writes j(t) into jpp[1-jold]; keep jc pointing at j(t)
       rc = enqueue_lb_kernel(h, h->src, tau, fs, 1 - h->jc, fl);
       if (rc == LBG_OK && j_missing) h->j_valid_step = h->t;
@@ -523,27 +555,20 @@ int ensure_collided(lbg_handle h, double tau, bool need_j) {
 
 int refresh_moments(lbg_handle h, double* pops_out) {
   if (h->phase != PH_LB) return fail(h, LBG_ERR_STATE, "no Lattice-Boltzmann state (call lbg_lb_init first)");
-  if (h->precollision) {
-    if (pops_out) return LBG_OK;  // caller copies f[src] directly
-    return LBG_OK;                // mom holds the state the driver set
-  }
+  if (h->precollision) return LBG_OK;  // mom / f[src] hold the state the driver set
   if (h->mom_valid_step == h->t && !pops_out) return LBG_OK;
-  Force fj = force_of_last_step(h);
-  double* scr = nullptr;
+  const Force& fj = force_of_last_step(h);
   MomArgs a{};
   a.geo = h->geo;
   a.fin = h->f[h->src];
-  a.mask = h->mask;
   a.mom = h->mom;
   a.pops = pops_out;
-  a.g_begin = own_begin(h);
-  a.g_end = own_end(h);
-  int mode = fj.mode;
+  a.fid_begin = own_begin(h);
+  a.fid_end = own_end(h);
   for (int d = 0; d < 3; ++d) a.fj[d] = fj.mode == FORCE_NONE ? 0.0 : fj.u[d];
   a.fj_field = fj.field;
   RET(wait_halo(h));
-  h->launches += launch_moments(a, mode, h->grid_lb, h->st);
-  (void)scr;
+  h->launches += launch_moments(a, fj.mode, h->grid_lb, h->st);
   h->mom_valid_step = h->t;
   return LBG_OK;
 }
@@ -554,20 +579,27 @@ int snapshot_prev_force(lbg_handle h) {
   for (int d = 0; d < 3; ++d) h->fprev.u[d] = h->fcur.u[d];
   if (h->fcur.mode == FORCE_FIELD) {
     RET(ensure_field(h, h->fprev));
-    CK(cudaMemcpyAsync(h->fprev.field, h->fcur.field, 3 * (size_t)h->geo.nalloc * sizeof(double),
+    CK(cudaMemcpyAsync(h->fprev.field, h->fcur.field, 3 * (size_t)h->geo.nfa * sizeof(double),
                        cudaMemcpyDeviceToDevice, h->st));
   }
   h->prev_equals_cur = false;
   return LBG_OK;
 }
 
-int copy_own_to_host(lbg_handle h, double* dst, const double* src_arr) {
-  CK(cudaMemcpyAsync(dst, src_arr + h->geo.plane, (size_t)h->nown * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+// compact array -> the driver's dense (i,j,k) array over the own planes (0 on solid nodes)
+int copy_own_to_host(lbg_handle h, double* dst, const double* arr) {
+  RET(ensure_stage(h));
+  h->launches += launch_scatter_to_dense(h->geo, arr, h->stage, h->st);
+  CK(cudaMemcpyAsync(dst, h->stage, (size_t)h->nown * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
   return LBG_OK;
 }
 
-int copy_own_to_device(lbg_handle h, double* dst_arr, const double* src) {
-  CK(cudaMemcpyAsync(dst_arr + h->geo.plane, src, (size_t)h->nown * sizeof(double), cudaMemcpyHostToDevice, h->st));
+int copy_own_to_device(lbg_handle h, double* arr, const double* src) {
+  RET(ensure_stage(h));
+  CK(cudaMemcpyAsync(h->stage, src, (size_t)h->nown * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  h->launches += launch_gather_from_dense(h->geo, h->stage, arr, h->st);
+  CK(cudaStreamSynchronize(h->st));
   return LBG_OK;
 }
 
@@ -649,12 +681,14 @@ int lbg_destroy(lbg_handle h) {
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->st_comm) cudaStreamSynchronize(h->st_comm);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  cudaFree(h->mask);
+  cudaFree(h->words);
+  cudaFree(h->gidx);
   cudaFree(h->f[0]);
   cudaFree(h->f[1]);
   cudaFree(h->mom);
   cudaFree(h->jpp[0]);
   cudaFree(h->jpp[1]);
+  cudaFree(h->stage);
   cudaFree(h->l2_slots);
   cudaFree(h->vacf_slots);
   cudaFree(h->partial);
@@ -679,7 +713,7 @@ int lbg_destroy(lbg_handle h) {
 int lbg_comm_unique_id(void* id_out) {
   lbg_handle h = nullptr;
   if (!id_out) return LBG_ERR_INVALID_ARG;
-  if (!g_nccl.load()) return fail(nullptr, LBG_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : ""));
+  if (!g_nccl.load()) return fail(nullptr, LBG_ERR_NCCL, "cannot load libnccl.so.2");
   ncclUniqueId id;
   static_assert(sizeof(ncclUniqueId) == LBG_UNIQUE_ID_BYTES, "ncclUniqueId size");
   NK(g_nccl.GetUniqueId(&id));
@@ -706,7 +740,7 @@ int lbg_get_interfacial(lbg_handle h, int8_t* out) {
   CK(cudaSetDevice(h->device));
   int8_t* d = nullptr;
   CK(cudaMalloc(&d, (size_t)h->nown));
-  h->launches += launch_extract_flag(h->geo, h->mask, MASK_INTERFACIAL, d, h->st);
+  h->launches += launch_dense_interfacial(h->geo, d, h->st);
   CK(cudaMemcpyAsync(out, d, (size_t)h->nown, cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
   cudaFree(d);
@@ -737,16 +771,21 @@ static void reset_lb_state(lbg_handle h) {
   h->force_version++;
 }
 
-int lbg_lb_init(lbg_handle h, double rho0) {
-  if (!h) return LBG_ERR_INVALID_ARG;
-  CK(cudaSetDevice(h->device));
-  const size_t nb = (size_t)h->geo.nalloc * sizeof(double);
+static int zero_lb_fields(lbg_handle h) {
+  const size_t nb = (size_t)h->geo.nfa * sizeof(double);
   CK(cudaMemsetAsync(h->f[0], 0, 19 * nb, h->st));
   CK(cudaMemsetAsync(h->f[1], 0, 19 * nb, h->st));
   CK(cudaMemsetAsync(h->mom, 0, 4 * nb, h->st));
   CK(cudaMemsetAsync(h->jpp[0], 0, 3 * nb, h->st));
   CK(cudaMemsetAsync(h->jpp[1], 0, 3 * nb, h->st));
-  h->launches += launch_lb_init(h->geo, h->mask, rho0, h->k.a0, h->f[0], h->mom, h->st);
+  return LBG_OK;
+}
+
+int lbg_lb_init(lbg_handle h, double rho0) {
+  if (!h) return LBG_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  RET(zero_lb_fields(h));
+  h->launches += launch_lb_init(h->geo, own_begin(h), own_end(h), rho0, h->k.a0, h->f[0], h->mom, h->st);
   CK(cudaGetLastError());
   reset_lb_state(h);
   return LBG_OK;
@@ -756,16 +795,10 @@ int lbg_lb_upload(lbg_handle h, const double* n, const double* rho, const double
                   const double* jz) {
   if (!h || !n || !rho || !jx || !jy || !jz) return LBG_ERR_INVALID_ARG;
   CK(cudaSetDevice(h->device));
-  const size_t nb = (size_t)h->geo.nalloc * sizeof(double);
-  CK(cudaMemsetAsync(h->f[0], 0, 19 * nb, h->st));
-  CK(cudaMemsetAsync(h->f[1], 0, 19 * nb, h->st));
-  CK(cudaMemsetAsync(h->mom, 0, 4 * nb, h->st));
-  CK(cudaMemsetAsync(h->jpp[0], 0, 3 * nb, h->st));
-  CK(cudaMemsetAsync(h->jpp[1], 0, 3 * nb, h->st));
-  for (int l = 0; l < 19; ++l) RET(copy_own_to_device(h, h->f[0] + (long long)l * h->geo.nalloc, n + (size_t)l * h->nown));
+  RET(zero_lb_fields(h));
+  for (int l = 0; l < 19; ++l) RET(copy_own_to_device(h, h->f[0] + (long long)l * h->geo.nfa, n + (size_t)l * h->nown));
   const double* m[4] = {rho, jx, jy, jz};
-  for (int c = 0; c < 4; ++c) RET(copy_own_to_device(h, h->mom + (long long)c * h->geo.nalloc, m[c]));
-  CK(cudaStreamSynchronize(h->st));
+  for (int c = 0; c < 4; ++c) RET(copy_own_to_device(h, h->mom + (long long)c * h->geo.nfa, m[c]));
   reset_lb_state(h);
   return LBG_OK;
 }
@@ -788,10 +821,9 @@ int lbg_lb_set_force_field(lbg_handle h, const double* fx, const double* fy, con
   CK(cudaSetDevice(h->device));
   RET(snapshot_prev_force(h));
   RET(ensure_field(h, h->fcur));
-  CK(cudaMemsetAsync(h->fcur.field, 0, 3 * (size_t)h->geo.nalloc * sizeof(double), h->st));
+  CK(cudaMemsetAsync(h->fcur.field, 0, 3 * (size_t)h->geo.nfa * sizeof(double), h->st));
   const double* src[3] = {fx, fy, fz};
-  for (int d = 0; d < 3; ++d) RET(copy_own_to_device(h, h->fcur.field + (long long)d * h->geo.nalloc, src[d]));
-  CK(cudaStreamSynchronize(h->st));
+  for (int d = 0; d < 3; ++d) RET(copy_own_to_device(h, h->fcur.field + (long long)d * h->geo.nfa, src[d]));
   h->fcur.mode = FORCE_FIELD;
   h->force_version++;
   return LBG_OK;
@@ -890,8 +922,7 @@ int lbg_lb_download_moments(lbg_handle h, double* rho, double* jx, double* jy, d
   RET(refresh_moments(h, nullptr));
   double* dst[4] = {rho, jx, jy, jz};
   for (int c = 0; c < 4; ++c)
-    if (dst[c]) RET(copy_own_to_host(h, dst[c], h->mom + (long long)c * h->geo.nalloc));
-  CK(cudaStreamSynchronize(h->st));
+    if (dst[c]) RET(copy_own_to_host(h, dst[c], h->mom + (long long)c * h->geo.nfa));
   return LBG_OK;
 }
 
@@ -908,8 +939,7 @@ int lbg_lb_download_populations(lbg_handle h, double* n) {
     h->collided_ok = false;
     from = h->f[1 - h->src];
   }
-  for (int l = 0; l < 19; ++l) RET(copy_own_to_host(h, n + (size_t)l * h->nown, from + (long long)l * h->geo.nalloc));
-  CK(cudaStreamSynchronize(h->st));
+  for (int l = 0; l < 19; ++l) RET(copy_own_to_host(h, n + (size_t)l * h->nown, from + (long long)l * h->geo.nfa));
   return LBG_OK;
 }
 
@@ -960,9 +990,16 @@ int lbg_lb_probe(lbg_handle h, int i, int j, int k, double out[4]) {
   CK(cudaSetDevice(h->device));
   RET(refresh_moments(h, nullptr));
   const long long g = (long long)i + (long long)h->geo.lx * j + (long long)h->geo.plane * (k + 1);
+  uint2 w;
+  CK(cudaMemcpyAsync(&w, h->words + (g >> 5), sizeof(w), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  const unsigned bit = (unsigned)(g & 31);
+  out[0] = out[1] = out[2] = out[3] = 0.0;  // solid node: everything is 0
+  if (!((w.x >> bit) & 1u)) return LBG_OK;
+  const long long fid = (long long)w.y + __builtin_popcount(w.x & ((1u << bit) - 1u));
   // out = jx, jy, jz, density
   for (int c = 0; c < 4; ++c)
-    CK(cudaMemcpyAsync(&out[c], h->mom + (long long)((c + 1) % 4) * h->geo.nalloc + g, sizeof(double),
+    CK(cudaMemcpyAsync(&out[c], h->mom + (long long)((c + 1) % 4) * h->geo.nfa + fid, sizeof(double),
                        cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
   return LBG_OK;
@@ -1005,26 +1042,25 @@ int lbg_mp_init(lbg_handle h, double Db, double ka, double kd, const double f_ex
   const double kBT = one / three;
   const double lambda = 4.0 * Db / kBT;
   // Phase B aliases the population buffers
-  const size_t nb = (size_t)g.nalloc * sizeof(double);
+  const size_t nb = (size_t)g.nfa * sizeof(double);
   h->q = h->f[0];
   h->s = h->f[1];
-  h->P[0] = h->f[1] + 4 * g.nalloc;
-  h->P[1] = h->f[1] + 7 * g.nalloc;
-  h->A[0] = h->f[1] + 10 * g.nalloc;
-  h->A[1] = h->f[1] + 13 * g.nalloc;
+  h->P[0] = h->f[1] + 4 * g.nfa;
+  h->P[1] = h->f[1] + 7 * g.nfa;
+  h->A[0] = h->f[1] + 10 * g.nfa;
+  h->A[1] = h->f[1] + 13 * g.nfa;
   CK(cudaMemsetAsync(h->f[1], 0, 19 * nb, h->st));
   CK(cudaMemsetAsync(h->mp_err, 0, sizeof(int), h->st));
   CK(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
   MPInitArgs a{};
   a.geo = g;
   a.k = h->k;
-  a.mask = h->mask;
   a.mom = h->mom;
   a.q = h->q;
   a.s = h->s;
   a.P0 = h->P[0];
-  a.g_begin = own_begin(h);
-  a.g_end = own_end(h);
+  a.fid_begin = own_begin(h);
+  a.fid_end = own_end(h);
   for (int d = 0; d < 3; ++d) a.f[d] = f_ext[d];
   for (int i = 0; i < 3; ++i) a.lambda_w[i] = lambda * h->k.a0[i];
   a.bw = 1.0 / Pstat;
@@ -1032,8 +1068,8 @@ int lbg_mp_init(lbg_handle h, double Db, double ka, double kd, const double f_ex
   a.ads = h->ads;
   a.partial = h->partial;
   a.err = h->mp_err;
-  const long long nblk = (h->nown + BLOCK - 1) / BLOCK;
-  const int grid = (int)(nblk < h->grid_mp ? nblk : h->grid_mp);
+  const long long nblk = (h->n_fluid + BLOCK - 1) / BLOCK;
+  const int grid = (int)(nblk < 1 ? 1 : (nblk < h->grid_mp ? nblk : h->grid_mp));
   h->launches += launch_mp_init(a, grid, h->st);
   std::vector<double> part((size_t)grid * 3);
   int bad = 0;
@@ -1078,6 +1114,8 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
   if (h->mp_bad) return fail(h, LBG_ERR_RESTPART_NEGATIVE, lbg_status_string(LBG_ERR_RESTPART_NEGATIVE));
   CK(cudaSetDevice(h->device));
   const Geo& g = h->geo;
+  const std::vector<long long>& ps = h->pstart;
+  const int nz = g.nzl;
   const double lim = 1.0 / (2.0 * g.lx * g.ly * h->lz_global / h->Db);
   auto is_conv = [&](long long it, const double* v) {
     return it > 2 && std::fabs(v[0]) < lim && std::fabs(v[1]) < lim && std::fabs(v[2]) < lim &&
@@ -1087,12 +1125,12 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
   while (total < nsteps) {
     const int chunk = (nsteps - total) < SLOT_CAP ? (nsteps - total) : SLOT_CAP;
     CK(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
+    CK(cudaMemsetAsync(h->vacf_slots, 0, (size_t)chunk * 3 * sizeof(double), h->st));
     int pc = h->pc;
     for (int i = 0; i < chunk; ++i) {
       const long long it = h->it + 1 + i;
       MPArgs a{};
       a.geo = g;
-      a.mask = h->mask;
       a.q = h->q;
       a.s = h->s;
       a.Pnow = h->P[pc];
@@ -1106,24 +1144,24 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
       a.partial = h->partial;
       a.vacf_slots = h->vacf_slots;
       a.batch_idx = i;
+      a.accumulate = 1;  // slots are zeroed per batch; every launch of a step adds its share
       a.check_prev = (i > 0 && (it - 1) > 2) ? 1 : 0;
       a.lim = lim;
       a.ctrl = h->ctrl;
       RET(wait_halo(h));
-      auto launch = [&](int pb, int pe, int accumulate) {
-        a.p_begin = pb;
-        a.p_end = pe;
-        a.accumulate = accumulate;
-        h->launches += launch_mp_step(a, h->mp_variant, h->grid_mp, h->st);
+      auto launch = [&](long long b, long long e) {
+        a.fid_begin = b;
+        a.fid_end = e;
+        h->launches += launch_mp_step(a, h->grid_mp, h->st);
       };
       if (h->nranks == 1) {
-        launch(1, g.nzl + 1, 0);
+        launch(own_begin(h), own_end(h));
       } else {
         const int all3[3] = {0, 1, 2};
-        launch(1, 2, 0);
-        if (g.nzl > 1) launch(g.nzl, g.nzl + 1, 1);
+        launch(ps[1], ps[2]);
+        if (nz > 1) launch(ps[nz], ps[nz + 1]);
         RET(halo_exchange(h, h->P[1 - pc], all3, 3, all3, 3));
-        if (g.nzl > 2) launch(2, g.nzl, 1);
+        if (nz > 2) launch(ps[2], ps[nz]);
         RET(wait_halo(h));
         RET(allreduce(h, h->vacf_slots + 3 * i, 3, ncclDouble, ncclSum));
       }
@@ -1161,17 +1199,15 @@ int lbg_mp_download(lbg_handle h, double* P, double* Pads) {
   if (h->phase != PH_MP) return fail(h, LBG_ERR_STATE, "lbg_mp_download needs lbg_mp_init first");
   CK(cudaSetDevice(h->device));
   RET(wait_halo(h));
-  double* d = nullptr;
-  CK(cudaMalloc(&d, (size_t)h->nown * 3 * sizeof(double)));
+  RET(ensure_stage(h));
   double* dst[2] = {P, Pads};
   double* src[2] = {h->P[h->pc], h->A[h->pc]};
   for (int c = 0; c < 2; ++c) {
     if (!dst[c]) continue;
-    h->launches += launch_soa_to_aos3(h->geo, src[c], d, h->st);
-    CK(cudaMemcpyAsync(dst[c], d, (size_t)h->nown * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    h->launches += launch_scatter3_to_dense_aos(h->geo, src[c], h->stage, h->st);
+    CK(cudaMemcpyAsync(dst[c], h->stage, (size_t)h->nown * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
   }
-  cudaFree(d);
   return LBG_OK;
 }
 

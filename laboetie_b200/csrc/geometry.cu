@@ -1,0 +1,223 @@
+// geometry.cu -- builds the fluid-compacted numbering from the driver's `nature` array, and moves
+// fields between the driver's dense (i,j,k) arrays and the compact storage.
+//
+// Replaces, on the device: detectInterfacialNodes (supercell_definition.f90:115-147) and the il/jl/kl
+// neighbour tables of equilibration.f90:109-119.
+#include <cub/block/block_scan.cuh>
+
+#include "lattice.cuh"
+
+namespace lbg {
+using namespace d3q19;
+
+namespace {
+
+// one warp per 32 dense nodes: fluid bits by ballot, count in .y (turned into a rank by the scan)
+__global__ void __launch_bounds__(BLOCK) build_bits_kernel(long long ndense, const int8_t* __restrict__ nat,
+                                                           uint2* __restrict__ words, long long nwords) {
+  const long long warp0 = ((long long)blockIdx.x * BLOCK + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * BLOCK) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long w = warp0; w < nwords; w += nwarps) {
+    const long long g = w * 32 + lane;
+    const bool fluid = (g < ndense) && (nat[g] == 0);  // module_system.f90:32: fluid = 0
+    const uint32_t b = __ballot_sync(0xffffffffu, fluid);
+    if (lane == 0) words[w] = make_uint2(b, (uint32_t)__popc(b));
+  }
+}
+
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = BLOCK * SCAN_ITEMS;
+
+// pass 1: per-tile totals of the counts; pass 3: exclusive scan inside each tile plus the tile offset
+__global__ void __launch_bounds__(BLOCK) scan_tile_sums_kernel(const uint2* __restrict__ words, long long nwords,
+                                                               unsigned long long* __restrict__ tile_sums) {
+  using BS = cub::BlockScan<unsigned int, BLOCK>;
+  __shared__ typename BS::TempStorage tmp;
+  const long long base = (long long)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  unsigned int v = 0;
+  for (int i = 0; i < SCAN_ITEMS; ++i)
+    if (base + i < nwords) v += words[base + i].y;
+  unsigned int incl, total;
+  BS(tmp).InclusiveSum(v, incl, total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(BLOCK) scan_tile_offsets_kernel(unsigned long long* __restrict__ tile_sums, int ntiles,
+                                                                  unsigned long long* __restrict__ total) {
+  // one block: serial over chunks of BLOCK tiles (ntiles is a few thousand at most)
+  using BS = cub::BlockScan<unsigned long long, BLOCK>;
+  __shared__ typename BS::TempStorage tmp;
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < ntiles; c0 += BLOCK) {
+    const int i = c0 + threadIdx.x;
+    const unsigned long long v = i < ntiles ? tile_sums[i] : 0ull;
+    unsigned long long excl, tot;
+    BS(tmp).ExclusiveSum(v, excl, tot);
+    if (i < ntiles) tile_sums[i] = carry + excl;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(BLOCK) scan_apply_kernel(uint2* __restrict__ words, long long nwords,
+                                                           const unsigned long long* __restrict__ tile_offsets) {
+  using BS = cub::BlockScan<unsigned int, BLOCK>;
+  __shared__ typename BS::TempStorage tmp;
+  const long long base = (long long)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  unsigned int c[SCAN_ITEMS], v = 0;
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    c[i] = (base + i < nwords) ? words[base + i].y : 0u;
+    v += c[i];
+  }
+  unsigned int excl;
+  BS(tmp).ExclusiveSum(v, excl);
+  unsigned int run = excl + (unsigned int)tile_offsets[blockIdx.x];
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < nwords) words[base + i].y = run;
+    run += c[i];
+  }
+}
+
+// interfacial flag of a dense node of an own plane: one of its 18 neighbours has the other nature.
+// The halo planes hold the true periodic neighbours, so z is not wrapped here.
+__device__ __forceinline__ bool node_interfacial(const Geo& geo, int g, bool me_fluid) {
+  Geo gz = geo;
+  gz.zwrap = 0;
+  const Nb nb = neighbours(gz, g);
+  bool itf = false;
+  static_for<1, NV>([&](auto Lc) {
+    constexpr int L = decltype(Lc)::value;
+    int fidn;
+    const bool other = lookup(geo, g + offset_plus<L>(nb), fidn);
+    itf = itf || (other != me_fluid);
+  });
+  return itf;
+}
+
+__global__ void __launch_bounds__(BLOCK) build_gidx_kernel(Geo geo, long long ndense, uint32_t* __restrict__ gidx) {
+  for (long long gg = (long long)blockIdx.x * BLOCK + threadIdx.x; gg < ndense; gg += (long long)gridDim.x * BLOCK) {
+    const int g = (int)gg;
+    int fid;
+    if (!lookup(geo, g, fid)) continue;
+    const int p = g / geo.plane;
+    uint32_t v = (uint32_t)g;
+    if (p >= 1 && p <= geo.nzl && node_interfacial(geo, g, true)) v |= GIDX_INTERFACIAL;
+    gidx[fid] = v;
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK) count_interfacial_kernel(Geo geo, long long fid_begin, long long fid_end,
+                                                                  unsigned long long* count) {
+  unsigned int n = 0;
+  for (long long f = fid_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; f < fid_end; f += (long long)gridDim.x * BLOCK)
+    n += (geo.gidx[f] & GIDX_INTERFACIAL) ? 1u : 0u;
+  n = __reduce_add_sync(0xffffffffu, n);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(count, (unsigned long long)n);
+}
+
+// supercell_definition.f90:115-147 for every node of the own planes (solid ones included)
+__global__ void __launch_bounds__(BLOCK) dense_interfacial_kernel(Geo geo, int8_t* __restrict__ out) {
+  const long long nown = (long long)geo.plane * geo.nzl;
+  for (long long q = (long long)blockIdx.x * BLOCK + threadIdx.x; q < nown; q += (long long)gridDim.x * BLOCK) {
+    const int g = (int)(q + geo.plane);
+    int fid;
+    const bool fl = lookup(geo, g, fid);
+    out[q] = node_interfacial(geo, g, fl) ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK) scatter_to_dense_kernel(Geo geo, const double* __restrict__ arr,
+                                                                 double* __restrict__ dense) {
+  const long long nown = (long long)geo.plane * geo.nzl;
+  for (long long q = (long long)blockIdx.x * BLOCK + threadIdx.x; q < nown; q += (long long)gridDim.x * BLOCK) {
+    int fid;
+    const bool fl = lookup(geo, (int)(q + geo.plane), fid);
+    dense[q] = fl ? arr[fid] : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK) gather_from_dense_kernel(Geo geo, const double* __restrict__ dense,
+                                                                  double* __restrict__ arr) {
+  const long long nown = (long long)geo.plane * geo.nzl;
+  for (long long q = (long long)blockIdx.x * BLOCK + threadIdx.x; q < nown; q += (long long)gridDim.x * BLOCK) {
+    int fid;
+    if (lookup(geo, (int)(q + geo.plane), fid)) arr[fid] = dense[q];
+  }
+}
+
+// three SoA arrays -> the reference's AoS (x:z,i,j,k) over the own planes
+__global__ void __launch_bounds__(BLOCK) scatter3_aos_kernel(Geo geo, const double* __restrict__ soa,
+                                                             double* __restrict__ aos) {
+  const long long nown = (long long)geo.plane * geo.nzl;
+  for (long long q = (long long)blockIdx.x * BLOCK + threadIdx.x; q < nown; q += (long long)gridDim.x * BLOCK) {
+    int fid;
+    const bool fl = lookup(geo, (int)(q + geo.plane), fid);
+    aos[3 * q + 0] = fl ? soa[fid] : 0.0;
+    aos[3 * q + 1] = fl ? soa[geo.nfa + fid] : 0.0;
+    aos[3 * q + 2] = fl ? soa[2 * geo.nfa + fid] : 0.0;
+  }
+}
+
+inline int big_grid(long long n) {
+  const long long b = (n + BLOCK - 1) / BLOCK;
+  return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
+}
+
+}  // namespace
+
+int launch_build_bits(int plane, int nzl, const int8_t* nature_halo, uint2* words, long long nwords, cudaStream_t st) {
+  const long long ndense = (long long)plane * (nzl + 2);
+  build_bits_kernel<<<big_grid(nwords * 32), BLOCK, 0, st>>>(ndense, nature_halo, words, nwords);
+  return 1;
+}
+
+int launch_scan_ranks(uint2* words, long long nwords, unsigned long long* total, cudaStream_t st) {
+  const int ntiles = (int)((nwords + SCAN_TILE - 1) / SCAN_TILE);
+  unsigned long long* tile_sums = nullptr;
+  cudaMallocAsync(&tile_sums, (size_t)ntiles * sizeof(unsigned long long), st);
+  scan_tile_sums_kernel<<<ntiles, BLOCK, 0, st>>>(words, nwords, tile_sums);
+  scan_tile_offsets_kernel<<<1, BLOCK, 0, st>>>(tile_sums, ntiles, total);
+  scan_apply_kernel<<<ntiles, BLOCK, 0, st>>>(words, nwords, tile_sums);
+  cudaFreeAsync(tile_sums, st);
+  return 3;
+}
+
+int launch_build_gidx(const Geo& g, long long nwords, uint32_t* gidx, cudaStream_t st) {
+  const long long ndense = (long long)g.plane * (g.nzl + 2);
+  (void)nwords;
+  build_gidx_kernel<<<big_grid(ndense), BLOCK, 0, st>>>(g, ndense, gidx);
+  return 1;
+}
+
+int launch_count_interfacial(const Geo& g, long long fid_begin, long long fid_end, unsigned long long* count,
+                             cudaStream_t st) {
+  count_interfacial_kernel<<<big_grid(fid_end - fid_begin), BLOCK, 0, st>>>(g, fid_begin, fid_end, count);
+  return 1;
+}
+
+int launch_dense_interfacial(const Geo& g, int8_t* out_own, cudaStream_t st) {
+  dense_interfacial_kernel<<<big_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, out_own);
+  return 1;
+}
+
+int launch_scatter_to_dense(const Geo& g, const double* arr, double* dense_own, cudaStream_t st) {
+  scatter_to_dense_kernel<<<big_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, arr, dense_own);
+  return 1;
+}
+
+int launch_gather_from_dense(const Geo& g, const double* dense_own, double* arr, cudaStream_t st) {
+  gather_from_dense_kernel<<<big_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, dense_own, arr);
+  return 1;
+}
+
+int launch_scatter3_to_dense_aos(const Geo& g, const double* soa3, double* dense_aos_own, cudaStream_t st) {
+  scatter3_aos_kernel<<<big_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, soa3, dense_aos_own);
+  return 1;
+}
+
+}  // namespace lbg

@@ -1,12 +1,10 @@
-// lb_kernels.cu -- Phase-A kernels for sm_100a: link masks, initial state,
-// the fused pull stream + moments + collide step, moments/population read-back,
-// plane profiles.
+// lb_kernels.cu -- Phase-A kernels for sm_100a: initial state, the fused pull stream + moments +
+// collide step, moments/population read-back, plane profiles.
 //
-// Data layout in HBM: structure of arrays, fp64, x fastest.  Population l of
-// node g lives at f[l*nalloc + g]; g = x + lx*(y + ly*p), p = plane index in the
-// slab including one halo plane on each z side.  One thread owns one node; a
-// warp covers 32 consecutive x, so every population access of a warp is one
-// contiguous 256-byte run (the +-x neighbours are the same run shifted by 8 B).
+// Data layout in HBM: fluid-compacted structure of arrays, fp64 (lbg_internal.h).  Population l of
+// fluid node fid lives at f[l*nfa + fid]; fids follow the reference's node order (x fastest), so a
+// warp's 32 consecutive fids are 32 consecutive fluid nodes of a row and every own-node access of a
+// warp is one aligned, fully used 256-byte run.  One thread owns one fluid node.
 //
 // The step kernel K(t) implements, for fluid node r (SURVEY 8a "A2 o A3"):
 //   n(t)(r,l)   = n*(t)(r-c_l, l)   if r-c_l is fluid          [streaming, equilibration.f90:227-243]
@@ -16,68 +14,16 @@
 // i.e. the reference's stream of step t fused with its collide of step t+1.
 // n* is written to the other buffer (two-lattice), so a step can be redone when
 // the driver changes the force after a convergence event.
-#include <type_traits>
+#include "lattice.cuh"
 
-#include "lbg_internal.h"
-
-#ifndef LBG_PREFETCH_MASK
-#define LBG_PREFETCH_MASK 1
-#endif
-#ifndef LBG_BLOCKED
-#define LBG_BLOCKED 0
-#endif
-// how the population loads go through the cache hierarchy: 0 = default (L1 allocating), 1 = .cg (L2 only),
-// 2 = .cs (streaming)
 #ifndef LBG_LOADMODE
-#define LBG_LOADMODE 1
+#define LBG_LOADMODE 1  // population loads: 0 default, 1 .cg (L2 only), 2 .cs (streaming); measured in profiles/
 #endif
 
 namespace lbg {
 using namespace d3q19;
 
 namespace {
-
-template <int L, int END, typename F>
-__device__ __forceinline__ void static_for(F&& f) {
-  if constexpr (L < END) {
-    f(std::integral_constant<int, L>{});
-    static_for<L + 1, END>(f);
-  }
-}
-
-// neighbour offsets of one node in the linear alloc index
-struct Nb {
-  int oxm, oxp, oym, oyp, ozm, ozp;
-};
-
-__device__ __forceinline__ Nb neighbours(const Geo& geo, int g) {
-  const int p = g / geo.plane;
-  const int rem = g - p * geo.plane;
-  const int y = rem / geo.lx;
-  const int x = rem - y * geo.lx;
-  Nb nb;
-  nb.oxm = (x == 0) ? (geo.lx - 1) : -1;
-  nb.oxp = (x == geo.lx - 1) ? -(geo.lx - 1) : 1;
-  nb.oym = (y == 0) ? (geo.ly - 1) * geo.lx : -geo.lx;
-  nb.oyp = (y == geo.ly - 1) ? -(geo.ly - 1) * geo.lx : geo.lx;
-  nb.ozm = (geo.zwrap && p == 1) ? (geo.nzl - 1) * geo.plane : -geo.plane;
-  nb.ozp = (geo.zwrap && p == geo.nzl) ? -(geo.nzl - 1) * geo.plane : geo.plane;
-  return nb;
-}
-
-// offset of node r + s*c_L (s = +1 or -1)
-template <int L, int S>
-__device__ __forceinline__ int offset(const Nb& nb) {
-  constexpr int X = S * cx(L), Y = S * cy(L), Z = S * cz(L);
-  int o = 0;
-  if constexpr (X > 0) o += nb.oxp;
-  if constexpr (X < 0) o += nb.oxm;
-  if constexpr (Y > 0) o += nb.oyp;
-  if constexpr (Y < 0) o += nb.oym;
-  if constexpr (Z > 0) o += nb.ozp;
-  if constexpr (Z < 0) o += nb.ozm;
-  return o;
-}
 
 __device__ __forceinline__ double ld_pop(const double* p) {
 #if LBG_LOADMODE == 1
@@ -89,18 +35,21 @@ __device__ __forceinline__ double ld_pop(const double* p) {
 #endif
 }
 
-// n(t)(r,·) by pull with halfway bounce-back.
-__device__ __forceinline__ void pull(const double* __restrict__ fin, long long nalloc, int g, uint32_t m, const Nb& nb,
+// n(t)(r,·) by pull with halfway bounce-back.  The source of direction L is node r - c_L = r + c_inv(L);
+// if it is solid the population comes back from the node's own opposite slot.
+__device__ __forceinline__ void pull(const Geo& geo, const double* __restrict__ fin, int fid, int g, const Nb& nb,
                                      double (&n)[NV]) {
+  const long long nfa = geo.nfa;
   static_for<0, NV>([&](auto Lc) {
     constexpr int L = decltype(Lc)::value;
     if constexpr (L == 0) {
-      n[0] = ld_pop(fin + g);
+      n[0] = ld_pop(fin + fid);
     } else {
-      const bool src_fluid = (m >> inv(L)) & 1u;  // r - c_L == r + c_inv(L)
-      const int idx = src_fluid ? g + offset<L, -1>(nb) : g;
+      int fsrc;
+      const bool src_fluid = lookup(geo, g + offset_plus<inv(L)>(nb), fsrc);
+      const int idx = src_fluid ? fsrc : fid;
       const int arr = src_fluid ? L : inv(L);
-      n[L] = ld_pop(fin + (long long)arr * nalloc + idx);
+      n[L] = ld_pop(fin + (long long)arr * nfa + idx);
     }
   });
 }
@@ -173,85 +122,8 @@ __device__ __forceinline__ void collide(double (&n)[NV], const Consts& k, double
   });
 }
 
-// True when the 32-byte sector (4 consecutive nodes, all arrays are 256-byte aligned and nalloc is a
-// multiple of 32) that holds node g contains a node with `bit` set.  Threads of such a sector all
-// store (zeros on solid nodes, which is what those nodes hold anyway): a fully written sector needs no
-// read-fill from HBM, a partially written one costs a DRAM read on top of the write.
-#ifndef LBG_FILL
-#define LBG_FILL 4  // nodes per fill group: 4 = one 32-byte sector
-#endif
-__device__ __forceinline__ bool sector_has(const uint32_t* __restrict__ mask, int g, uint32_t bit) {
-  const uint4* p = reinterpret_cast<const uint4*>(mask + (g & ~(LBG_FILL - 1)));
-  uint32_t any = 0;
-#pragma unroll
-  for (int i = 0; i < LBG_FILL / 4; ++i) {
-    const uint4 mm = __ldg(p + i);
-    any |= mm.x | mm.y | mm.z | mm.w;
-  }
-  return (any & bit) != 0;
-}
-
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
-// One fluid node of K(t): pull, moments, convergence / negativity bookkeeping, collide, store.
-template <bool TAU1, int FMODE, bool CHECK, bool WRITEJ>
-__device__ __forceinline__ void lb_fluid_node(const LBArgs& a, int g, uint32_t m, double& dmax, bool& any_neg) {
-  const long long nalloc = a.geo.nalloc;
-  const Nb nb = neighbours(a.geo, g);
-  double n[NV];
-  pull(a.fin, nalloc, g, m, nb, n);
-  double fjx = 0, fjy = 0, fjz = 0, fcx = 0, fcy = 0, fcz = 0;
-  if constexpr (FMODE == FORCE_UNIFORM) {
-    fjx = a.fj[0]; fjy = a.fj[1]; fjz = a.fj[2];
-    fcx = a.fc[0]; fcy = a.fc[1]; fcz = a.fc[2];
-  } else if constexpr (FMODE == FORCE_FIELD) {
-    fjx = a.fj_field[g]; fjy = a.fj_field[nalloc + g]; fjz = a.fj_field[2 * nalloc + g];
-    fcx = a.fc_field[g]; fcy = a.fc_field[nalloc + g]; fcz = a.fc_field[2 * nalloc + g];
-  }
-  double rho, jx, jy, jz;
-  bool neg;
-  moments(n, fjx / 2.0, fjy / 2.0, fjz / 2.0, rho, jx, jy, jz, neg);
-  any_neg |= neg;
-  if constexpr (CHECK) {
-    const double ox = a.jold[g], oy = a.jold[nalloc + g], oz = a.jold[2 * nalloc + g];
-    dmax = fmax(dmax, fmax(fabs(jx - ox), fmax(fabs(jy - oy), fabs(jz - oz))));
-  }
-  if constexpr (WRITEJ) {
-    a.jnew[g] = jx;
-    a.jnew[nalloc + g] = jy;
-    a.jnew[2 * nalloc + g] = jz;
-  }
-  collide<TAU1, FMODE != FORCE_NONE>(n, a.k, rho, jx, jy, jz, fcx, fcy, fcz, a.w1, a.w2, a.w3);
-  static_for<0, NV>([&](auto Lc) {
-    constexpr int L = decltype(Lc)::value;
-    a.fout[(long long)L * nalloc + g] = n[L];
-  });
-}
-
-// A solid node that shares a 32-byte sector with a fluid node stores its zeros (populations and j are 0
-// on solid nodes, init_simu.f90:32-39), so the sector is written whole and needs no read-fill from HBM.
-template <bool WRITEJ>
-__device__ __forceinline__ void lb_fill_node(const LBArgs& a, int g) {
-  const long long nalloc = a.geo.nalloc;
-  if constexpr (WRITEJ) {
-    a.jnew[g] = 0.0;
-    a.jnew[nalloc + g] = 0.0;
-    a.jnew[2 * nalloc + g] = 0.0;
-  }
-  static_for<0, NV>([&](auto Lc) {
-    constexpr int L = decltype(Lc)::value;
-    a.fout[(long long)L * nalloc + g] = 0.0;
-  });
-}
-
 // ---------------------------------------------------------------------------
-// MINB = resident blocks per SM the register allocation aims at: 3 (80 registers) keeps more loads in
-// flight on mostly-fluid lattices, 2 (124 registers, no spills) is faster on porous ones, where solid
-// lanes idle and instruction issue, not memory latency, is the co-limiter.
+// MINB = resident blocks per SM the register allocation aims at.
 template <bool TAU1, int FMODE, bool CHECK, bool WRITEJ, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_constant__ LBArgs a) {
   __shared__ int s_stop;
@@ -274,40 +146,48 @@ __global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_const
   if (s_stop) return;
 
   const Geo& geo = a.geo;
-  const long long nalloc = geo.nalloc;
+  const long long nfa = geo.nfa;
   double dmax = 0.0;
   bool any_neg = false;
-  // tiles of BLOCK consecutive nodes; the mask word of the next tile is fetched one iteration ahead so
-  // that its DRAM latency does not sit in front of the 22 dependent population loads
-  const int ntiles = (int)((a.g_end - a.g_begin + BLOCK - 1) / BLOCK);
-#if LBG_BLOCKED
-  const int tpb = (ntiles + gridDim.x - 1) / gridDim.x;
-  const int t_first = blockIdx.x * tpb, t_last = min(ntiles, t_first + tpb), t_step = 1;
-#else
-  const int t_first = blockIdx.x, t_last = ntiles, t_step = gridDim.x;
-#endif
-  auto node_of = [&](int tile) { return a.g_begin + (long long)tile * BLOCK + threadIdx.x; };
-#if LBG_PREFETCH_MASK
-  uint32_t m_next = 0;
-  if (t_first < t_last && node_of(t_first) < a.g_end) m_next = __ldg(a.mask + node_of(t_first));
-#endif
-  for (int tile = t_first; tile < t_last; tile += t_step) {
-    const long long gg = node_of(tile);
-#if LBG_PREFETCH_MASK
-    const uint32_t m = m_next;
-    {
-      const int tn = tile + t_step;
-      m_next = (tn < t_last && node_of(tn) < a.g_end) ? __ldg(a.mask + node_of(tn)) : 0u;
+  // tiles of BLOCK consecutive fluid nodes; the dense index of the next tile's node is fetched one
+  // iteration ahead so that its DRAM latency does not sit in front of the dependent population loads
+  const long long first = a.fid_begin + (long long)blockIdx.x * BLOCK + threadIdx.x;
+  const long long stride = (long long)gridDim.x * BLOCK;
+  uint32_t gi_next = first < a.fid_end ? __ldg(geo.gidx + first) : 0u;
+  for (long long ff = first; ff < a.fid_end; ff += stride) {
+    const uint32_t gi = gi_next;
+    if (ff + stride < a.fid_end) gi_next = __ldg(geo.gidx + ff + stride);
+    const int fid = (int)ff;
+    const int g = (int)(gi & GIDX_MASK);
+    const Nb nb = neighbours(geo, g);
+    double n[NV];
+    pull(geo, a.fin, fid, g, nb, n);
+    double fjx = 0, fjy = 0, fjz = 0, fcx = 0, fcy = 0, fcz = 0;
+    if constexpr (FMODE == FORCE_UNIFORM) {
+      fjx = a.fj[0]; fjy = a.fj[1]; fjz = a.fj[2];
+      fcx = a.fc[0]; fcy = a.fc[1]; fcz = a.fc[2];
+    } else if constexpr (FMODE == FORCE_FIELD) {
+      fjx = a.fj_field[fid]; fjy = a.fj_field[nfa + fid]; fjz = a.fj_field[2 * nfa + fid];
+      fcx = a.fc_field[fid]; fcy = a.fc_field[nfa + fid]; fcz = a.fc_field[2 * nfa + fid];
     }
-    if (gg >= a.g_end) continue;
-    const int g = (int)gg;
-#else
-    if (gg >= a.g_end) continue;
-    const int g = (int)gg;
-    const uint32_t m = __ldg(a.mask + g);
-#endif
-    if (m & MASK_FLUID) lb_fluid_node<TAU1, FMODE, CHECK, WRITEJ>(a, g, m, dmax, any_neg);
-    else if (sector_has(a.mask, g, MASK_FLUID)) lb_fill_node<WRITEJ>(a, g);
+    double rho, jx, jy, jz;
+    bool neg;
+    moments(n, fjx / 2.0, fjy / 2.0, fjz / 2.0, rho, jx, jy, jz, neg);
+    any_neg |= neg;
+    if constexpr (CHECK) {
+      const double ox = a.jold[fid], oy = a.jold[nfa + fid], oz = a.jold[2 * nfa + fid];
+      dmax = fmax(dmax, fmax(fabs(jx - ox), fmax(fabs(jy - oy), fabs(jz - oz))));
+    }
+    if constexpr (WRITEJ) {
+      a.jnew[fid] = jx;
+      a.jnew[nfa + fid] = jy;
+      a.jnew[2 * nfa + fid] = jz;
+    }
+    collide<TAU1, FMODE != FORCE_NONE>(n, a.k, rho, jx, jy, jz, fcx, fcy, fcz, a.w1, a.w2, a.w3);
+    static_for<0, NV>([&](auto Lc) {
+      constexpr int L = decltype(Lc)::value;
+      a.fout[(long long)L * nfa + fid] = n[L];
+    });
   }
   if (any_neg) s_neg = 1;
   if constexpr (CHECK) {
@@ -327,278 +207,92 @@ __global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_const
   }
 }
 
-// Porous lattices: the same step with block-level compaction.  A block takes a super-tile of
-// CT_NODES consecutive nodes, turns its mask words into a list of fluid nodes (ballot-free prefix
-// sums over 8-node groups) and a list of fill nodes in shared memory, and then every lane works on a
-// fluid node.  Without this a warp on a 60 %-fluid lattice runs with ~19 of 32 lanes active and the
-// kernel is bound by instruction issue and exposed latency rather than by HBM.  Per-node arithmetic
-// is the shared lb_fluid_node(), so results are identical to lb_step_kernel.
-constexpr int CT_PER_THREAD = 8;
-constexpr int CT_NODES = BLOCK * CT_PER_THREAD;
-
-template <bool TAU1, int FMODE, bool CHECK, bool WRITEJ>
-__global__ void __launch_bounds__(BLOCK, 2) lb_step_compact_kernel(const __grid_constant__ LBArgs a) {
-  __shared__ int s_stop;
-  __shared__ double s_red[BLOCK / 32];
-  __shared__ int s_neg;
-  __shared__ uint32_t s_mask[CT_NODES];
-  __shared__ unsigned short s_fluid[CT_NODES];
-  __shared__ unsigned short s_fill[CT_NODES];
-  __shared__ int s_wsum[2][BLOCK / 32];
-  __shared__ int s_tot[2];
-  if (threadIdx.x == 0) {
-    int stop = *(volatile int*)&a.ctrl->stop | *(volatile int*)&a.ctrl->neg_step_idx;
-    if (!stop && a.prev_checked && a.prev_may_stop) {
-      const double prev = __longlong_as_double((long long)*(volatile unsigned long long*)&a.l2_slots[a.batch_idx - 1]);
-      if (prev <= a.target) {  // equilibration.f90:346
-        a.ctrl->stop = 1;
-        a.ctrl->stop_idx = a.batch_idx;
-        stop = 1;
-      }
-    }
-    s_stop = stop;
-    s_neg = 0;
-  }
-  __syncthreads();
-  if (s_stop) return;
-
-  double dmax = 0.0;
-  bool any_neg = false;
-  const long long g_lo = a.g_begin & ~7LL;  // super-tiles start on an 8-node boundary (uint4 mask loads)
-  const int ntiles = (int)((a.g_end - g_lo + CT_NODES - 1) / CT_NODES);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  auto load_masks = [&](int tile, uint32_t (&mk)[CT_PER_THREAD]) {
-    const long long g0 = g_lo + (long long)tile * CT_NODES + threadIdx.x * CT_PER_THREAD;
-#pragma unroll
-    for (int i = 0; i < CT_PER_THREAD; ++i) mk[i] = 0;
-    if (tile < ntiles && g0 < a.g_end) {  // nalloc is padded, so the vector loads stay inside the array
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(a.mask + g0));
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.mask + g0 + 4));
-      mk[0] = u.x; mk[1] = u.y; mk[2] = u.z; mk[3] = u.w;
-      mk[4] = v.x; mk[5] = v.y; mk[6] = v.z; mk[7] = v.w;
-#pragma unroll
-      for (int i = 0; i < CT_PER_THREAD; ++i)
-        if (g0 + i < a.g_begin || g0 + i >= a.g_end) mk[i] = 0;  // outside this launch's range
-    }
-  };
-
-  uint32_t mk[CT_PER_THREAD], mk_next[CT_PER_THREAD];
-  load_masks(blockIdx.x, mk_next);
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-#pragma unroll
-    for (int i = 0; i < CT_PER_THREAD; ++i) mk[i] = mk_next[i];
-    load_masks(tile + gridDim.x, mk_next);  // one super-tile ahead
-    // --- phase 1: lists of fluid nodes and of fill nodes (solid, in a sector with a fluid node)
-    int nf = 0, nz = 0;
-    const bool g0_has = ((mk[0] | mk[1] | mk[2] | mk[3]) & MASK_FLUID) != 0;
-    const bool g1_has = ((mk[4] | mk[5] | mk[6] | mk[7]) & MASK_FLUID) != 0;
-#pragma unroll
-    for (int i = 0; i < CT_PER_THREAD; ++i) {
-      const bool fl = mk[i] & MASK_FLUID;
-      nf += fl ? 1 : 0;
-      nz += (!fl && (i < 4 ? g0_has : g1_has)) ? 1 : 0;
-    }
-    // the part of the range outside [g_begin, g_end) must not be filled either
-    {
-      const long long g0 = g_lo + (long long)tile * CT_NODES + threadIdx.x * CT_PER_THREAD;
-      int nz2 = 0;
-#pragma unroll
-      for (int i = 0; i < CT_PER_THREAD; ++i) {
-        const bool fl = mk[i] & MASK_FLUID;
-        const bool inside = (g0 + i >= a.g_begin) && (g0 + i < a.g_end);
-        nz2 += (!fl && inside && (i < 4 ? g0_has : g1_has)) ? 1 : 0;
-      }
-      nz = nz2;
-    }
-    int pf = nf, pz = nz;  // inclusive warp scans
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int tf = __shfl_up_sync(0xffffffffu, pf, o), tz = __shfl_up_sync(0xffffffffu, pz, o);
-      if (lane >= o) {
-        pf += tf;
-        pz += tz;
-      }
-    }
-    if (lane == 31) {
-      s_wsum[0][warp] = pf;
-      s_wsum[1][warp] = pz;
-    }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-      int acc = 0;
-      for (int w = 0; w < BLOCK / 32; ++w) {
-        const int v = s_wsum[threadIdx.x][w];
-        s_wsum[threadIdx.x][w] = acc;
-        acc += v;
-      }
-      s_tot[threadIdx.x] = acc;
-    }
-    __syncthreads();
-    {
-      int of = s_wsum[0][warp] + pf - nf, oz = s_wsum[1][warp] + pz - nz;
-      const long long g0 = g_lo + (long long)tile * CT_NODES + threadIdx.x * CT_PER_THREAD;
-#pragma unroll
-      for (int i = 0; i < CT_PER_THREAD; ++i) {
-        const int off = threadIdx.x * CT_PER_THREAD + i;
-        s_mask[off] = mk[i];
-        const bool fl = mk[i] & MASK_FLUID;
-        const bool inside = (g0 + i >= a.g_begin) && (g0 + i < a.g_end);
-        if (fl) s_fluid[of++] = (unsigned short)off;
-        else if (inside && (i < 4 ? g0_has : g1_has)) s_fill[oz++] = (unsigned short)off;
-      }
-    }
-    __syncthreads();
-    // --- phase 2: every lane on a fluid node
-    const int tot_f = s_tot[0], tot_z = s_tot[1];
-    const long long base = g_lo + (long long)tile * CT_NODES;
-    for (int i = threadIdx.x; i < tot_f; i += BLOCK) {
-      const int off = s_fluid[i];
-      lb_fluid_node<TAU1, FMODE, CHECK, WRITEJ>(a, (int)(base + off), s_mask[off], dmax, any_neg);
-    }
-    for (int i = threadIdx.x; i < tot_z; i += BLOCK) lb_fill_node<WRITEJ>(a, (int)(base + s_fill[i]));
-    __syncthreads();  // lists are rebuilt by the next super-tile
-  }
-  if (any_neg) s_neg = 1;
-  if constexpr (CHECK) {
-    dmax = warp_max(dmax);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = dmax;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if constexpr (CHECK) {
-      double v = s_red[0];
-#pragma unroll
-      for (int w = 1; w < BLOCK / 32; ++w) v = fmax(v, s_red[w]);
-      atomicMax(&a.l2_slots[a.batch_idx], (unsigned long long)__double_as_longlong(v));
-    }
-    if (s_neg) atomicCAS(&a.ctrl->neg_step_idx, 0, a.batch_idx + 1);
-  }
-}
-
 template <bool TAU1, int FMODE>
 __global__ void __launch_bounds__(BLOCK) collide_kernel(const __grid_constant__ CollideArgs a) {
-  const long long nalloc = a.geo.nalloc;
-  for (long long gg = a.g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; gg < a.g_end;
-       gg += (long long)gridDim.x * BLOCK) {
-    const int g = (int)gg;
-    const uint32_t m = __ldg(a.mask + g);
+  const long long nfa = a.geo.nfa;
+  for (long long ff = a.fid_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; ff < a.fid_end;
+       ff += (long long)gridDim.x * BLOCK) {
+    const int fid = (int)ff;
     double n[NV];
     static_for<0, NV>([&](auto Lc) {
       constexpr int L = decltype(Lc)::value;
-      n[L] = a.fin[(long long)L * nalloc + g];
+      n[L] = a.fin[(long long)L * nfa + fid];
     });
-    if (m & MASK_FLUID) {
-      double fcx = 0, fcy = 0, fcz = 0;
-      if constexpr (FMODE == FORCE_UNIFORM) {
-        fcx = a.fc[0]; fcy = a.fc[1]; fcz = a.fc[2];
-      } else if constexpr (FMODE == FORCE_FIELD) {
-        fcx = a.fc_field[g]; fcy = a.fc_field[nalloc + g]; fcz = a.fc_field[2 * nalloc + g];
-      }
-      collide<TAU1, FMODE != FORCE_NONE>(n, a.k, a.mom[g], a.mom[nalloc + g], a.mom[2 * nalloc + g],
-                                         a.mom[3 * nalloc + g], fcx, fcy, fcz, a.w1, a.w2, a.w3);
+    double fcx = 0, fcy = 0, fcz = 0;
+    if constexpr (FMODE == FORCE_UNIFORM) {
+      fcx = a.fc[0]; fcy = a.fc[1]; fcz = a.fc[2];
+    } else if constexpr (FMODE == FORCE_FIELD) {
+      fcx = a.fc_field[fid]; fcy = a.fc_field[nfa + fid]; fcz = a.fc_field[2 * nfa + fid];
     }
+    collide<TAU1, FMODE != FORCE_NONE>(n, a.k, a.mom[fid], a.mom[nfa + fid], a.mom[2 * nfa + fid], a.mom[3 * nfa + fid],
+                                       fcx, fcy, fcz, a.w1, a.w2, a.w3);
     static_for<0, NV>([&](auto Lc) {
       constexpr int L = decltype(Lc)::value;
-      a.fout[(long long)L * nalloc + g] = n[L];
+      a.fout[(long long)L * nfa + fid] = n[L];
     });
   }
 }
 
 template <int FMODE>
 __global__ void __launch_bounds__(BLOCK) moments_kernel(const __grid_constant__ MomArgs a) {
-  const long long nalloc = a.geo.nalloc;
-  for (long long gg = a.g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; gg < a.g_end;
-       gg += (long long)gridDim.x * BLOCK) {
-    const int g = (int)gg;
-    const uint32_t m = __ldg(a.mask + g);
+  const long long nfa = a.geo.nfa;
+  for (long long ff = a.fid_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; ff < a.fid_end;
+       ff += (long long)gridDim.x * BLOCK) {
+    const int fid = (int)ff;
+    const int g = (int)(a.geo.gidx[fid] & GIDX_MASK);
+    const Nb nb = neighbours(a.geo, g);
     double n[NV];
-    double rho = 0, jx = 0, jy = 0, jz = 0;
-    if (m & MASK_FLUID) {
-      const Nb nb = neighbours(a.geo, g);
-      pull(a.fin, nalloc, g, m, nb, n);
-      double fjx = 0, fjy = 0, fjz = 0;
-      if constexpr (FMODE == FORCE_UNIFORM) {
-        fjx = a.fj[0]; fjy = a.fj[1]; fjz = a.fj[2];
-      } else if constexpr (FMODE == FORCE_FIELD) {
-        fjx = a.fj_field[g]; fjy = a.fj_field[nalloc + g]; fjz = a.fj_field[2 * nalloc + g];
-      }
-      bool neg;
-      moments(n, fjx / 2.0, fjy / 2.0, fjz / 2.0, rho, jx, jy, jz, neg);
-    } else {
-      static_for<0, NV>([&](auto Lc) { n[decltype(Lc)::value] = 0.0; });
+    pull(a.geo, a.fin, fid, g, nb, n);
+    double fjx = 0, fjy = 0, fjz = 0;
+    if constexpr (FMODE == FORCE_UNIFORM) {
+      fjx = a.fj[0]; fjy = a.fj[1]; fjz = a.fj[2];
+    } else if constexpr (FMODE == FORCE_FIELD) {
+      fjx = a.fj_field[fid]; fjy = a.fj_field[nfa + fid]; fjz = a.fj_field[2 * nfa + fid];
     }
+    double rho, jx, jy, jz;
+    bool neg;
+    moments(n, fjx / 2.0, fjy / 2.0, fjz / 2.0, rho, jx, jy, jz, neg);
     if (a.mom) {
-      a.mom[g] = rho;
-      a.mom[nalloc + g] = jx;
-      a.mom[2 * nalloc + g] = jy;
-      a.mom[3 * nalloc + g] = jz;
+      a.mom[fid] = rho;
+      a.mom[nfa + fid] = jx;
+      a.mom[2 * nfa + fid] = jy;
+      a.mom[3 * nfa + fid] = jz;
     }
     if (a.pops) {
       static_for<0, NV>([&](auto Lc) {
         constexpr int L = decltype(Lc)::value;
-        a.pops[(long long)L * nalloc + g] = n[L];
+        a.pops[(long long)L * nfa + fid] = n[L];
       });
     }
   }
 }
 
-// supercell_definition.f90:115-147 + the neighbour tables of equilibration.f90:109-119,
-// folded into one word per node.  nature has valid halo planes.
-__global__ void __launch_bounds__(BLOCK) build_mask_kernel(Geo geo, const int8_t* __restrict__ nat,
-                                                           uint32_t* __restrict__ mask) {
-  const long long g_begin = geo.plane, g_end = (long long)geo.plane * (geo.nzl + 1);
-  for (long long gg = g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; gg < g_end;
-       gg += (long long)gridDim.x * BLOCK) {
-    const int g = (int)gg;
-    Geo gz = geo;
-    gz.zwrap = 0;  // nature carries real halo planes
-    const Nb nb = neighbours(gz, g);
-    const int8_t me = nat[g];
-    uint32_t m = (me == 0) ? MASK_FLUID : 0u;
-    bool interfacial = false;
-    static_for<1, NV>([&](auto Lc) {
-      constexpr int L = decltype(Lc)::value;
-      const int8_t other = nat[g + offset<L, +1>(nb)];
-      if (other == 0) m |= (1u << L);
-      interfacial = interfacial || (other != me);
-    });
-    if (interfacial) m |= MASK_INTERFACIAL;
-    mask[g] = m;
-  }
-}
-
-// init_simu.f90:24-39 and equilibration.f90:59,75-80
-__global__ void __launch_bounds__(BLOCK) lb_init_kernel(Geo geo, const uint32_t* __restrict__ mask, double rho0,
+// init_simu.f90:24-39 and equilibration.f90:59,75-80 (solid nodes hold 0 and own no storage)
+__global__ void __launch_bounds__(BLOCK) lb_init_kernel(long long nfa, long long fid_begin, long long fid_end, double rho0,
                                                         double a00, double a01, double a02, double* __restrict__ f,
                                                         double* __restrict__ mom) {
-  const long long g_begin = geo.plane, g_end = (long long)geo.plane * (geo.nzl + 1);
   const double a0[3] = {a00, a01, a02};
-  for (long long g = g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; g < g_end;
-       g += (long long)gridDim.x * BLOCK) {
-    const double dens = (mask[g] & MASK_FLUID) ? rho0 : 0.0;
+  for (long long fid = fid_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; fid < fid_end;
+       fid += (long long)gridDim.x * BLOCK) {
     static_for<0, NV>([&](auto Lc) {
       constexpr int L = decltype(Lc)::value;
-      f[(long long)L * geo.nalloc + g] = dens * a0[kind(L)];
+      f[(long long)L * nfa + fid] = rho0 * a0[kind(L)];
     });
-    mom[g] = dens;
-    mom[geo.nalloc + g] = 0.0;
-    mom[2 * geo.nalloc + g] = 0.0;
-    mom[3 * geo.nalloc + g] = 0.0;
+    mom[fid] = rho0;
+    mom[nfa + fid] = 0.0;
+    mom[2 * nfa + fid] = 0.0;
+    mom[3 * nfa + fid] = 0.0;
   }
 }
 
 // equilibration.f90:381-386 materialised as a field (used when a uniform force
 // and a force field meet across a force change).
-__global__ void __launch_bounds__(BLOCK) fill_force_kernel(Geo geo, const uint32_t* __restrict__ mask, double fx,
-                                                           double fy, double fz, double* __restrict__ field) {
-  const long long g_begin = geo.plane, g_end = (long long)geo.plane * (geo.nzl + 1);
-  for (long long g = g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; g < g_end;
-       g += (long long)gridDim.x * BLOCK) {
-    const bool fl = mask[g] & MASK_FLUID;
-    field[g] = fl ? fx : 0.0;
-    field[geo.nalloc + g] = fl ? fy : 0.0;
-    field[2 * geo.nalloc + g] = fl ? fz : 0.0;
+__global__ void __launch_bounds__(BLOCK) fill_force_kernel(long long nfa, long long nf, double fx, double fy, double fz,
+                                                           double* __restrict__ field) {
+  for (long long fid = (long long)blockIdx.x * BLOCK + threadIdx.x; fid < nf; fid += (long long)gridDim.x * BLOCK) {
+    field[fid] = fx;
+    field[nfa + fid] = fy;
+    field[2 * nfa + fid] = fz;
   }
 }
 
@@ -614,12 +308,14 @@ __global__ void __launch_bounds__(BLOCK) profile_kernel(const __grid_constant__ 
     const int i = a.axis == 0 ? p : c;
     const int j = a.axis == 0 ? c : (a.axis == 1 ? p : b);
     const int kk = a.axis == 2 ? p : b;
-    const long long g = (long long)i + (long long)geo.lx * j + (long long)geo.plane * (kk + 1);
-    const double d = a.mom[g];
+    const int g = i + geo.lx * j + geo.plane * (kk + 1);
+    int fid;
+    if (!lookup(geo, g, fid)) continue;  // solid: density and momentum are 0
+    const double d = a.mom[fid];
     sd += d;
-    sx += a.mom[geo.nalloc + g];
-    sy += a.mom[2 * geo.nalloc + g];
-    sz += a.mom[3 * geo.nalloc + g];
+    sx += a.mom[geo.nfa + fid];
+    sy += a.mom[2 * geo.nfa + fid];
+    sz += a.mom[3 * geo.nfa + fid];
     cnt += (d > a.eps) ? 1.0 : 0.0;
   }
   __shared__ double red[5][BLOCK];
@@ -634,72 +330,11 @@ __global__ void __launch_bounds__(BLOCK) profile_kernel(const __grid_constant__ 
   if (threadIdx.x < 5) a.out[(long long)p * 5 + threadIdx.x] = red[threadIdx.x][0];
 }
 
-__global__ void __launch_bounds__(BLOCK) count_flags_kernel(Geo geo, const uint32_t* __restrict__ mask,
-                                                            unsigned long long* counts) {
-  const long long g_begin = geo.plane, g_end = (long long)geo.plane * (geo.nzl + 1);
-  unsigned int nf = 0, nif = 0;
-  for (long long g = g_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; g < g_end;
-       g += (long long)gridDim.x * BLOCK) {
-    const uint32_t m = mask[g];
-    if (m & MASK_FLUID) {
-      ++nf;
-      if (m & MASK_INTERFACIAL) ++nif;
-    }
-  }
-  nf = __reduce_add_sync(0xffffffffu, nf);
-  nif = __reduce_add_sync(0xffffffffu, nif);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&counts[0], (unsigned long long)nf);
-    atomicAdd(&counts[1], (unsigned long long)nif);
-  }
-}
-
-__global__ void __launch_bounds__(BLOCK) extract_flag_kernel(Geo geo, const uint32_t* __restrict__ mask, uint32_t bit,
-                                                             int8_t* __restrict__ out) {
-  const long long nown = (long long)geo.plane * geo.nzl;
-  for (long long q = (long long)blockIdx.x * BLOCK + threadIdx.x; q < nown; q += (long long)gridDim.x * BLOCK)
-    out[q] = (mask[q + geo.plane] & bit) ? 1 : 0;
-}
-
 inline int small_grid(long long n) {
   long long b = (n + BLOCK - 1) / BLOCK;
   return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
 }
 
-}  // namespace
-
-int launch_build_mask(const Geo& g, const int8_t* nature_halo, uint32_t* mask, cudaStream_t st) {
-  build_mask_kernel<<<small_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, nature_halo, mask);
-  return 1;
-}
-
-int launch_lb_init(const Geo& g, const uint32_t* mask, double rho0, const double a0[3], double* f, double* mom,
-                   cudaStream_t st) {
-  lb_init_kernel<<<small_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, mask, rho0, a0[0], a0[1], a0[2], f, mom);
-  return 1;
-}
-
-int launch_fill_force(const Geo& g, const uint32_t* mask, const double f[3], double* field, cudaStream_t st) {
-  fill_force_kernel<<<small_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, mask, f[0], f[1], f[2], field);
-  return 1;
-}
-
-int launch_count_flags(const Geo& g, const uint32_t* mask, unsigned long long* counts2, cudaStream_t st) {
-  count_flags_kernel<<<small_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, mask, counts2);
-  return 1;
-}
-
-int launch_extract_flag(const Geo& g, const uint32_t* mask, uint32_t bit, int8_t* out_own, cudaStream_t st) {
-  extract_flag_kernel<<<small_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, mask, bit, out_own);
-  return 1;
-}
-
-int launch_profile(const ProfileArgs& a, int rows, cudaStream_t st) {
-  profile_kernel<<<rows, BLOCK, 0, st>>>(a);
-  return 1;
-}
-
-namespace {
 template <bool TAU1, int FMODE, int MINB>
 void launch_step_cw(const LBArgs& a, bool check, bool writej, int grid, cudaStream_t st) {
   if (check) lb_step_kernel<TAU1, FMODE, true, true, MINB><<<grid, BLOCK, 0, st>>>(a);
@@ -718,37 +353,32 @@ void launch_collide_f(const CollideArgs& a, int fmode, int grid, cudaStream_t st
   else if (fmode == FORCE_UNIFORM) collide_kernel<TAU1, FORCE_UNIFORM><<<grid, BLOCK, 0, st>>>(a);
   else collide_kernel<TAU1, FORCE_FIELD><<<grid, BLOCK, 0, st>>>(a);
 }
-int clamp_grid(long long n, int grid) {
-  const long long b = (n + BLOCK - 1) / BLOCK;
-  return (int)(b < 1 ? 1 : (b < grid ? b : grid));
-}
+
 }  // namespace
 
-namespace {
-template <bool TAU1, int FMODE>
-void launch_compact_cw(const LBArgs& a, bool check, bool writej, int grid, cudaStream_t st) {
-  if (check) lb_step_compact_kernel<TAU1, FMODE, true, true><<<grid, BLOCK, 0, st>>>(a);
-  else if (writej) lb_step_compact_kernel<TAU1, FMODE, false, true><<<grid, BLOCK, 0, st>>>(a);
-  else lb_step_compact_kernel<TAU1, FMODE, false, false><<<grid, BLOCK, 0, st>>>(a);
+int launch_lb_init(const Geo& g, long long fid_begin, long long fid_end, double rho0, const double a0[3], double* f,
+                   double* mom, cudaStream_t st) {
+  if (fid_end <= fid_begin) return 0;
+  lb_init_kernel<<<small_grid(fid_end - fid_begin), BLOCK, 0, st>>>(g.nfa, fid_begin, fid_end, rho0, a0[0], a0[1], a0[2],
+                                                                    f, mom);
+  return 1;
 }
-template <bool TAU1>
-void launch_compact_f(const LBArgs& a, int fmode, bool check, bool writej, int grid, cudaStream_t st) {
-  if (fmode == FORCE_NONE) launch_compact_cw<TAU1, FORCE_NONE>(a, check, writej, grid, st);
-  else if (fmode == FORCE_UNIFORM) launch_compact_cw<TAU1, FORCE_UNIFORM>(a, check, writej, grid, st);
-  else launch_compact_cw<TAU1, FORCE_FIELD>(a, check, writej, grid, st);
+
+int launch_fill_force(const Geo& g, long long nf, const double f[3], double* field, cudaStream_t st) {
+  if (nf <= 0) return 0;
+  fill_force_kernel<<<small_grid(nf), BLOCK, 0, st>>>(g.nfa, nf, f[0], f[1], f[2], field);
+  return 1;
 }
-}  // namespace
+
+int launch_profile(const ProfileArgs& a, int rows, cudaStream_t st) {
+  profile_kernel<<<rows, BLOCK, 0, st>>>(a);
+  return 1;
+}
 
 int launch_lb_step(const LBArgs& a, bool tau1, int fmode, bool check, bool writej, int minb, int grid,
                    cudaStream_t st) {
-  if (minb == 0) {  // block-compacting kernel for porous lattices
-    const long long nt = (a.g_end - (a.g_begin & ~7LL) + CT_NODES - 1) / CT_NODES;
-    const int gr = (int)(nt < 1 ? 1 : (nt < grid ? nt : grid));
-    if (tau1) launch_compact_f<true>(a, fmode, check, writej, gr, st);
-    else launch_compact_f<false>(a, fmode, check, writej, gr, st);
-    return 1;
-  }
-  const int gr = clamp_grid(a.g_end - a.g_begin, grid);
+  if (a.fid_end <= a.fid_begin) return 0;
+  const int gr = clamp_grid(a.fid_end - a.fid_begin, grid);
   if (minb >= 3) {
     if (tau1) launch_step_f<true, 3>(a, fmode, check, writej, gr, st);
     else launch_step_f<false, 3>(a, fmode, check, writej, gr, st);
@@ -760,14 +390,16 @@ int launch_lb_step(const LBArgs& a, bool tau1, int fmode, bool check, bool write
 }
 
 int launch_collide(const CollideArgs& a, bool tau1, int fmode, int grid, cudaStream_t st) {
-  const int gr = clamp_grid(a.g_end - a.g_begin, grid);
+  if (a.fid_end <= a.fid_begin) return 0;
+  const int gr = clamp_grid(a.fid_end - a.fid_begin, grid);
   if (tau1) launch_collide_f<true>(a, fmode, gr, st);
   else launch_collide_f<false>(a, fmode, gr, st);
   return 1;
 }
 
 int launch_moments(const MomArgs& a, int fmode, int grid, cudaStream_t st) {
-  const int gr = clamp_grid(a.g_end - a.g_begin, grid);
+  if (a.fid_end <= a.fid_begin) return 0;
+  const int gr = clamp_grid(a.fid_end - a.fid_begin, grid);
   if (fmode == FORCE_NONE) moments_kernel<FORCE_NONE><<<gr, BLOCK, 0, st>>>(a);
   else if (fmode == FORCE_UNIFORM) moments_kernel<FORCE_UNIFORM><<<gr, BLOCK, 0, st>>>(a);
   else moments_kernel<FORCE_FIELD><<<gr, BLOCK, 0, st>>>(a);
@@ -776,9 +408,7 @@ int launch_moments(const MomArgs& a, int fmode, int grid, cudaStream_t st) {
 
 int occupancy_grid_lb(int sm_count, int minb) {
   int per_sm = 0;
-  if (minb == 0)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lb_step_compact_kernel<true, FORCE_UNIFORM, true, true>, BLOCK, 0);
-  else if (minb >= 3)
+  if (minb >= 3)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lb_step_kernel<true, FORCE_UNIFORM, true, true, 3>, BLOCK, 0);
   else
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lb_step_kernel<true, FORCE_UNIFORM, true, true, 2>, BLOCK, 0);

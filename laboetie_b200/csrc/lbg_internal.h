@@ -1,4 +1,21 @@
 // lbg_internal.h -- shared between the kernel translation units and api.cu.
+//
+// Storage: fluid-compacted structure of arrays.  The lattice nodes of a slab (own planes plus one
+// halo plane on each z side) are numbered in the reference's memory order, g = x + lx*(y + ly*p);
+// the fluid nodes among them are numbered consecutively in that same order (x fastest), fid = 0..NF-1.
+// Every field is a set of arrays indexed by fid with a common stride nfa.  Solid nodes own no storage:
+// their populations are 0 for ever (init_simu.f90:32-39, the swap rule of equilibration.f90:204-222)
+// and nothing ever reads them.  Consequences for HBM traffic: every 32-byte sector a warp touches
+// is full of fluid data, stores are whole sectors with all 32 lanes active, and a porous lattice moves
+// only its fluid bytes.  A plane's fluid nodes are one contiguous fid range, so the z-halo planes stay
+// contiguous runs that NCCL can send without packing.
+//
+// The map between the two numberings is a rank structure over the dense order, 8 bytes per 32 nodes:
+//   words[w] = { bits: fluid bit of nodes 32w..32w+31,  rank: number of fluid nodes before node 32w }
+//   fid(g)   = rank + popc(bits & lower_mask(g & 31))            (one 8-byte load, L1/L2 resident)
+//   gidx[fid] = g | interfacial << 31                            (4 bytes per fluid node, streamed)
+// It replaces the il/jl/kl neighbour tables of equilibration.f90:109-119 and the per-node flags of
+// supercell_definition.f90:115-147.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -10,18 +27,14 @@
 namespace lbg {
 
 constexpr int BLOCK = 256;
+constexpr uint32_t GIDX_MASK = 0x7fffffffu;
+constexpr uint32_t GIDX_INTERFACIAL = 0x80000000u;
 
-// mask word per node: bit 0 = node is fluid; bit l (1..18) = node r+c_l is fluid;
-// bit 19 = node is interfacial (supercell_definition.f90:115-147).
-constexpr uint32_t MASK_FLUID = 1u;
-constexpr uint32_t MASK_INTERFACIAL = 1u << 19;
-
-// Slab geometry.  Arrays carry one halo plane below (plane 0) and one above
-// (plane nzl+1); own planes are 1..nzl.  With zwrap (single slab) the halo
-// planes of the fields are unused and z neighbours wrap inside the kernel.
 struct Geo {
   int lx, ly, plane, nzl, zwrap;
-  long long nalloc;  // plane * (nzl + 2)
+  long long nfa;          // stride of every per-fluid-node array (multiple of 32 elements)
+  const uint2* words;     // {bits, rank} per 32 dense nodes over planes 0..nzl+1
+  const uint32_t* gidx;   // per fid: dense index, bit 31 = interfacial
 };
 
 // Device-side control block: lets a batch of step kernels stop itself at the
@@ -38,14 +51,13 @@ enum ForceMode { FORCE_NONE = 0, FORCE_UNIFORM = 1, FORCE_FIELD = 2 };
 struct LBArgs {
   Geo geo;
   d3q19::Consts k;
-  const double* fin;   // 19 arrays, stride geo.nalloc: post-collision populations n*(t)
+  const double* fin;   // 19 arrays, stride geo.nfa: post-collision populations n*(t)
   double* fout;        // n*(t+1)
-  const uint32_t* mask;
-  long long g_begin, g_end;  // linear alloc index range to process
+  long long fid_begin, fid_end;  // fluid nodes to process
   double w1, w2, w3;         // 1-1/tau, 1/tau, 1-1/(2 tau)
   double fj[3];              // uniform force in effect for step t (enters j as f/2)
   double fc[3];              // uniform force of the collision that follows
-  const double* fj_field;    // 3 arrays, stride nalloc (FORCE_FIELD)
+  const double* fj_field;    // 3 arrays, stride nfa (FORCE_FIELD)
   const double* fc_field;
   const double* jold;        // 3 arrays: j(t-1)
   double* jnew;              // 3 arrays: j(t)
@@ -62,9 +74,8 @@ struct CollideArgs {
   d3q19::Consts k;
   const double* fin;  // pre-collision n(t)
   double* fout;
-  const uint32_t* mask;
-  const double* mom;  // rho, jx, jy, jz: 4 arrays, stride nalloc
-  long long g_begin, g_end;
+  const double* mom;  // rho, jx, jy, jz: 4 arrays, stride nfa
+  long long fid_begin, fid_end;
   double w1, w2, w3;
   double fc[3];
   const double* fc_field;
@@ -73,10 +84,9 @@ struct CollideArgs {
 struct MomArgs {
   Geo geo;
   const double* fin;  // n*(t)
-  const uint32_t* mask;
   double* mom;        // out: rho, jx, jy, jz
-  double* pops;       // out (optional): n(t), 19 arrays stride nalloc
-  long long g_begin, g_end;
+  double* pops;       // out (optional): n(t), 19 arrays stride nfa
+  long long fid_begin, fid_end;
   double fj[3];
   const double* fj_field;
 };
@@ -84,12 +94,11 @@ struct MomArgs {
 struct MPInitArgs {
   Geo geo;
   d3q19::Consts k;
-  const uint32_t* mask;
-  const double* mom;   // rho, jx, jy, jz with valid halos (or zwrap)
+  const double* mom;   // rho, jx, jy, jz with valid halo ranges (or zwrap)
   double* q;           // 18 arrays: incoming link probabilities q_l(r) = p_{inv l}(r + c_l)
   double* s;           // 4 arrays: remaining fraction (after -ka where adsorbing), u*_x, u*_y, u*_z
   double* P0;          // 3 arrays: Propagated_Quantity(:, now) at t=0
-  long long g_begin, g_end;
+  long long fid_begin, fid_end;
   double f[3];
   double lambda_w[3];  // lambda * w per kind
   double bw;           // 1 / Pstat
@@ -101,21 +110,19 @@ struct MPInitArgs {
 
 struct MPArgs {
   Geo geo;
-  const uint32_t* mask;
   const double* q;
   const double* s;
   const double* Pnow;   // 3 arrays
   double* Pnext;
   const double* Anow;   // adsorbed, 3 arrays
   double* Anext;
-  int p_begin, p_end;   // plane range [p_begin, p_end) to process (own planes are 1..nzl)
+  long long fid_begin, fid_end;
   double ka, kd, one_minus_kd;
   int ads;
   double* partial;      // per block partial vacf (3 each)
   double* vacf_slots;   // 3 per batch step
   int batch_idx;
-  int accumulate;       // add into the slot instead of overwriting (second launch of a split step)
-  int nblocks_total;
+  int accumulate;       // add into the slot instead of overwriting (later launch of a split step)
   int check_prev;       // evaluate the convergence criterion on slot batch_idx-1
   double lim;           // 1/(2 lx ly lz / Db)
   Ctrl* ctrl;
@@ -129,22 +136,29 @@ struct ProfileArgs {
   double* out;  // 5 per row: sum jx, jy, jz, sum rho, count(rho > eps)
 };
 
-// launchers (lb_kernels.cu / mp_kernels.cu).  Each returns the number of kernels launched.
-int launch_build_mask(const Geo& g, const int8_t* nature_halo, uint32_t* mask, cudaStream_t st);
-int launch_lb_init(const Geo& g, const uint32_t* mask, double rho0, const double a0[3], double* f, double* mom,
-                   cudaStream_t st);
+// launchers (geometry.cu / lb_kernels.cu / mp_kernels.cu).  Each returns the number of kernels launched.
+int launch_build_bits(int plane, int nzl, const int8_t* nature_halo, uint2* words, long long nwords, cudaStream_t st);
+int launch_scan_ranks(uint2* words, long long nwords, unsigned long long* total, cudaStream_t st);
+int launch_build_gidx(const Geo& g, long long nwords, uint32_t* gidx, cudaStream_t st);
+int launch_count_interfacial(const Geo& g, long long fid_begin, long long fid_end, unsigned long long* count,
+                             cudaStream_t st);
+int launch_dense_interfacial(const Geo& g, int8_t* out_own, cudaStream_t st);
+// dense <-> compact transfers over own planes (dense index relative to the first own plane)
+int launch_scatter_to_dense(const Geo& g, const double* arr, double* dense_own, cudaStream_t st);
+int launch_gather_from_dense(const Geo& g, const double* dense_own, double* arr, cudaStream_t st);
+int launch_scatter3_to_dense_aos(const Geo& g, const double* soa3, double* dense_aos_own, cudaStream_t st);
+
+int launch_lb_init(const Geo& g, long long fid_begin, long long fid_end, double rho0, const double a0[3], double* f,
+                   double* mom, cudaStream_t st);
 int launch_collide(const CollideArgs& a, bool tau1, int fmode, int grid, cudaStream_t st);
 int launch_lb_step(const LBArgs& a, bool tau1, int fmode, bool check, bool writej, int minb, int grid,
                    cudaStream_t st);
 int launch_moments(const MomArgs& a, int fmode, int grid, cudaStream_t st);
-int launch_fill_force(const Geo& g, const uint32_t* mask, const double f[3], double* field, cudaStream_t st);
+int launch_fill_force(const Geo& g, long long nf, const double f[3], double* field, cudaStream_t st);
 int launch_profile(const ProfileArgs& a, int rows, cudaStream_t st);
-int launch_count_flags(const Geo& g, const uint32_t* mask, unsigned long long* counts2, cudaStream_t st);
-int launch_extract_flag(const Geo& g, const uint32_t* mask, uint32_t bit, int8_t* out_own, cudaStream_t st);
 int launch_mp_init(const MPInitArgs& a, int grid, cudaStream_t st);
-int launch_mp_step(const MPArgs& a, int variant, int grid, cudaStream_t st);
-int launch_soa_to_aos3(const Geo& g, const double* soa, double* aos_own, cudaStream_t st);
+int launch_mp_step(const MPArgs& a, int grid, cudaStream_t st);
 int occupancy_grid_lb(int sm_count, int minb);
-int occupancy_grid_mp(int sm_count, int variant);
+int occupancy_grid_mp(int sm_count);
 
 }  // namespace lbg
