@@ -732,6 +732,12 @@ int lbg_comm_init(lbg_handle h, int nranks, int rank, const void* id) {
   NK(g_nccl.CommInitRank(&h->comm, nranks, uid, rank));
   h->nranks = nranks;
   h->rank = rank;
+  // The LB step kernel is persistent (one wave of resident blocks).  NCCL's send/recv kernel needs SM
+  // room to run beside the interior planes' kernel, otherwise the exchange waits for that kernel to end:
+  // leave 32 block slots free (measured at N=2: 7.7 -> 6.2 ms per step; profiles/multigpu_r1.txt).
+  int reserve = 32;
+  if (const char* e = std::getenv("LBG_GRID_RESERVE")) reserve = std::atoi(e);
+  if (reserve > 0 && reserve < h->grid_lb) h->grid_lb -= reserve;
   return LBG_OK;
 }
 
