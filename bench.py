@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--also", default="cfg2,cfg3", help="extra single-GPU workloads reported under 'also' (N=1 only)")
     return ap.parse_args()
 
 
@@ -296,6 +297,34 @@ def run_ours(args):
                "seconds": t_e2e,
                "what": "create(H2D geometry)+lb_init+K LB steps(l2err history D2H)+moments D2H(pinned)+mp_init+K MP steps(vacf D2H); fixed costs amortised over K"}
 
+    # ---- the other BASELINE configurations that fit one GPU, device-resident numbers only (N=1) ------
+    also = {}
+    if nranks == 1 and args.also:
+        hbm0, _ = peaks()
+        for wl in [w for w in args.also.split(",") if w and w != args.workload]:
+            try:
+                nat2, (ax, ay, az), _, f2, desc2, _ = build_geometry(wl, 0, 1)
+                with lb.LaboetieGPU(nat2, device=local) as s2:
+                    nf2, nif2 = s2.counts()
+                    s2.lb_init(1.0)
+                    s2.lb_set_force_uniform(f2)
+                    s2.lb_step(W, tau=TAU, check_every=ce, target_error=-1.0, want_history=False)
+                    s2.sync(); s2.timer_start()
+                    s2.lb_step(4 * K, tau=TAU, check_every=ce, target_error=-1.0, want_history=False)
+                    tl = s2.timer_stop() / (4 * K)
+                    s2.mp_init(TRACER["Db"], TRACER["ka"], TRACER["kd"], f2)
+                    s2.mp_step(W, want_history=False)
+                    s2.sync(); s2.timer_start()
+                    s2.mp_step(4 * K, want_history=False)
+                    tm = s2.timer_stop() / (4 * K)
+                bl, bm = algorithmic_bytes(nf2, nif2, nat2.size, ce == 1)
+                also[wl] = {"description": desc2, "lattice": [ax, ay, az], "fluid_fraction": nf2 / nat2.size,
+                            "value": nat2.size / ((tl + tm) * 1e-3) / 1e6, "lb_mlups": nat2.size / (tl * 1e-3) / 1e6,
+                            "mp_mlups": nat2.size / (tm * 1e-3) / 1e6, "lb_roofline_frac": bl / (tl * 1e-3) / 1e9 / hbm0,
+                            "mp_roofline_frac": bm / (tm * 1e-3) / 1e9 / hbm0, "steps": 4 * K}
+            except Exception as e:  # noqa: BLE001
+                also[wl] = {"error": str(e)}
+
     if rank != 0:
         return
     hbm, peak_src = peaks()
@@ -320,6 +349,8 @@ def run_ours(args):
                      "mp_step_kernel": {"achieved": mp_gbs, "frac": mp_gbs / hbm, "algorithmic_bytes_per_launch": b_mp}},
         "gpu_launches": int(l_lb + l_mp), "clocks": clocks,
     }
+    if also:
+        line["also"] = also
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu_baseline:
