@@ -98,6 +98,7 @@ struct lbg_handle_s {
   ncclComm_t comm = nullptr;
   cudaStream_t st = nullptr, st_comm = nullptr;
   cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_ar[2] = {nullptr, nullptr};  // lagged vacf all-reduces of Phase B
   bool halo_pending = false;
 
   uint2* words = nullptr;
@@ -312,15 +313,17 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   CKB(cudaStreamCreateWithFlags(&h->st_comm, cudaStreamNonBlocking));
   CKB(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
   CKB(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+  CKB(cudaEventCreateWithFlags(&h->ev_ar[0], cudaEventDisableTiming));
+  CKB(cudaEventCreateWithFlags(&h->ev_ar[1], cudaEventDisableTiming));
   CKB(cudaEventCreate(&h->ev_t0));
   CKB(cudaEventCreate(&h->ev_t1));
   h->grid_mp = occupancy_grid_mp(h->sm_count);
-  CKB(cudaMalloc(&h->l2_slots, SLOT_CAP * sizeof(unsigned long long)));
+  CKB(cudaMalloc(&h->l2_slots, 2 * SLOT_CAP * sizeof(unsigned long long)));
   CKB(cudaMalloc(&h->vacf_slots, 3 * SLOT_CAP * sizeof(double)));
   CKB(cudaMalloc(&h->ctrl, sizeof(Ctrl)));
   CKB(cudaMalloc(&h->mp_err, sizeof(int)));
   CKB(cudaMalloc(&h->counts, 2 * sizeof(unsigned long long)));
-  CKB(cudaMallocHost(&h->h_l2, SLOT_CAP * sizeof(unsigned long long)));
+  CKB(cudaMallocHost(&h->h_l2, 2 * SLOT_CAP * sizeof(unsigned long long)));
   CKB(cudaMallocHost(&h->h_vacf, 3 * SLOT_CAP * sizeof(double)));
   CKB(cudaMallocHost(&h->h_ctrl, sizeof(Ctrl)));
   CKB(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
@@ -481,11 +484,10 @@ int enqueue_lb_kernel(lbg_handle h, int fin, double tau, const ForceSel& fs, int
     RET(halo_exchange(h, h->f[1 - fin], UP_L, 5, DOWN_L, 5));
     if (nz > 2) launch(ps[2], ps[nz]);
     if (fl.check) {
-      // global max of l2err, and the negative-population flag, before the next step looks at them
+      // global max of l2err and of the negative-population flag (one all-reduce of the slot pair),
+      // before the next step looks at them
       RET(wait_halo(h));
-      RET(allreduce(h, h->l2_slots + fl.batch_idx, 1, ncclUint64, ncclMax));
-      RET(wait_halo(h));
-      RET(allreduce(h, &h->ctrl->neg_step_idx, 1, ncclInt32, ncclMax));
+      RET(allreduce(h, h->l2_slots + 2 * fl.batch_idx, 2, ncclUint64, ncclMax));
     }
   }
   return LBG_OK;
@@ -702,6 +704,8 @@ int lbg_destroy(lbg_handle h) {
   cudaFreeHost(h->h_ctrl);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   if (h->ev_halo) cudaEventDestroy(h->ev_halo);
+  if (h->ev_ar[0]) cudaEventDestroy(h->ev_ar[0]);
+  if (h->ev_ar[1]) cudaEventDestroy(h->ev_ar[1]);
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
   if (h->st) cudaStreamDestroy(h->st);
@@ -853,7 +857,7 @@ int lbg_lb_step(lbg_handle h, double tau, int nsteps, int check_every, double ta
   int total = 0;
   while (total < nsteps) {
     const int chunk = (nsteps - total) < SLOT_CAP ? (nsteps - total) : SLOT_CAP;
-    CK(cudaMemsetAsync(h->l2_slots, 0, (size_t)chunk * sizeof(unsigned long long), h->st));
+    CK(cudaMemsetAsync(h->l2_slots, 0, 2 * (size_t)chunk * sizeof(unsigned long long), h->st));
     CK(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
     RET(ensure_collided(h, tau, checked(h->t + 1)));
     ForceSel fs;
@@ -874,20 +878,22 @@ int lbg_lb_step(lbg_handle h, double tau, int nsteps, int check_every, double ta
       jold = 1 - jold;
     }
     RET(wait_halo(h));
-    CK(cudaMemcpyAsync(h->h_l2, h->l2_slots, (size_t)chunk * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(h->h_l2, h->l2_slots, 2 * (size_t)chunk * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st));
     CK(cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     CK(cudaGetLastError());
     if (scr) cudaFree(scr);
     int executed = chunk, conv = 0, neg = 0;
-    if (h->h_ctrl->neg_step_idx) {
-      executed = h->h_ctrl->neg_step_idx;
-      neg = 1;
-    }
+    for (int i = 0; i < chunk; ++i)
+      if (h->h_l2[2 * i + 1]) {  // without a check the flag is local to this slab; with check_every=1 it is global
+        executed = i + 1;
+        neg = 1;
+        break;
+      }
     for (int i = 0; i < executed; ++i) {
       const long long s = h->t + 1 + i;
       double v = std::numeric_limits<double>::quiet_NaN();
-      if (checked(s)) std::memcpy(&v, &h->h_l2[i], sizeof(double));
+      if (checked(s)) std::memcpy(&v, &h->h_l2[2 * i], sizeof(double));
       if (l2err_hist) l2err_hist[total + i] = v;
       if (neg && i == executed - 1) break;  // the reference stops before l2err on that step
       if (checked(s) && s > 2 && v <= target_error) {  // equilibration.f90:346
@@ -1133,6 +1139,10 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
     CK(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
     CK(cudaMemsetAsync(h->vacf_slots, 0, (size_t)chunk * 3 * sizeof(double), h->st));
     int pc = h->pc;
+    // The stop test needs the global vacf of a step.  On one GPU step i looks at step i-1.  Across GPUs
+    // the all-reduce of step i is left a whole step to complete: step i looks at step i-2, so at most
+    // one step runs past the converged one -- and its input buffers are exactly the wanted state.
+    const int lag = h->nranks > 1 ? 2 : 1;
     for (int i = 0; i < chunk; ++i) {
       const long long it = h->it + 1 + i;
       MPArgs a{};
@@ -1151,7 +1161,7 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
       a.vacf_slots = h->vacf_slots;
       a.batch_idx = i;
       a.accumulate = 1;  // slots are zeroed per batch; every launch of a step adds its share
-      a.check_prev = (i > 0 && (it - 1) > 2) ? 1 : 0;
+      a.check_slot = (i - lag >= 0 && (it - lag) > 2) ? i - lag : -1;
       a.lim = lim;
       a.ctrl = h->ctrl;
       RET(wait_halo(h));
@@ -1164,32 +1174,43 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
         launch(own_begin(h), own_end(h));
       } else {
         const int all3[3] = {0, 1, 2};
+        if (i >= 2) CK(cudaStreamWaitEvent(h->st, h->ev_ar[i & 1], 0));  // all-reduce of step i-2
         launch(ps[1], ps[2]);
         if (nz > 1) launch(ps[nz], ps[nz + 1]);
         RET(halo_exchange(h, h->P[1 - pc], all3, 3, all3, 3));
         if (nz > 2) launch(ps[2], ps[nz]);
-        RET(wait_halo(h));
-        RET(allreduce(h, h->vacf_slots + 3 * i, 3, ncclDouble, ncclSum));
+        // all-reduce of this step's vacf on the communication stream, not waited for here
+        CK(cudaEventRecord(h->ev_ready, h->st));
+        CK(cudaStreamWaitEvent(h->st_comm, h->ev_ready, 0));
+        NK(g_nccl.AllReduce(h->vacf_slots + 3 * i, h->vacf_slots + 3 * i, 3, ncclDouble, ncclSum, h->comm, h->st_comm));
+        CK(cudaEventRecord(h->ev_ar[i & 1], h->st_comm));
       }
       pc = 1 - pc;
     }
     RET(wait_halo(h));
+    if (h->nranks > 1) {
+      CK(cudaStreamWaitEvent(h->st, h->ev_ar[0], 0));
+      CK(cudaStreamWaitEvent(h->st, h->ev_ar[1], 0));
+    }
     CK(cudaMemcpyAsync(h->h_vacf, h->vacf_slots, (size_t)chunk * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     CK(cudaGetLastError());
-    int executed = chunk, conv = 0;
+    int executed = chunk, conv = 0, ran = chunk;
     for (int i = 0; i < chunk; ++i) {
       const long long it = h->it + 1 + i;
       if (vacf)
         for (int d = 0; d < 3; ++d) vacf[(size_t)(total + i) * 3 + d] = h->h_vacf[(size_t)i * 3 + d];
       if (is_conv(it, h->h_vacf + (size_t)i * 3)) {
-        executed = i + 1;
+        executed = i + 1;                                  // steps the reference would have made
+        ran = (i + lag < chunk) ? i + lag : chunk;         // step kernels that actually ran
         conv = 1;
         break;
       }
     }
+    // `ran` kernels flipped the buffers; a kernel that ran past the converged step left its input intact
+    if (ran & 1) h->pc = 1 - h->pc;
+    if ((ran - executed) & 1) h->pc = 1 - h->pc;
     h->it += executed;
-    if (executed & 1) h->pc = 1 - h->pc;
     total += executed;
     if (steps_done) *steps_done = total;
     if (conv) {

@@ -130,9 +130,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_const
   __shared__ double s_red[BLOCK / 32];
   __shared__ int s_neg;
   if (threadIdx.x == 0) {
-    int stop = *(volatile int*)&a.ctrl->stop | *(volatile int*)&a.ctrl->neg_step_idx;
+    // slot pair of a step: [2i] = l2err bits, [2i+1] = non-zero if a population went negative
+    int stop = *(volatile int*)&a.ctrl->stop;
+    if (!stop && a.batch_idx > 0 && *(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 1) + 1] != 0ull) {
+      a.ctrl->stop = 1;  // equilibration.f90:248: the reference stops at the step with a negative population
+      stop = 1;
+    }
     if (!stop && a.prev_checked && a.prev_may_stop) {
-      const double prev = __longlong_as_double((long long)*(volatile unsigned long long*)&a.l2_slots[a.batch_idx - 1]);
+      const double prev =
+          __longlong_as_double((long long)*(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 1)]);
       if (prev <= a.target) {  // equilibration.f90:346
         a.ctrl->stop = 1;
         a.ctrl->stop_idx = a.batch_idx;  // 1 + index of the converged step
@@ -201,9 +207,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_const
 #pragma unroll
       for (int w = 1; w < BLOCK / 32; ++w) v = fmax(v, s_red[w]);
       // non-negative doubles order like their bit patterns
-      atomicMax(&a.l2_slots[a.batch_idx], (unsigned long long)__double_as_longlong(v));
+      atomicMax(&a.l2_slots[2 * a.batch_idx], (unsigned long long)__double_as_longlong(v));
     }
-    if (s_neg) atomicCAS(&a.ctrl->neg_step_idx, 0, a.batch_idx + 1);
+    if (s_neg) atomicMax(&a.l2_slots[2 * a.batch_idx + 1], 1ull);
   }
 }
 

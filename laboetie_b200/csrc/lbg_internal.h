@@ -61,7 +61,7 @@ struct LBArgs {
   const double* fc_field;
   const double* jold;        // 3 arrays: j(t-1)
   double* jnew;              // 3 arrays: j(t)
-  unsigned long long* l2_slots;  // one per batch step, bit pattern of a non-negative double
+  unsigned long long* l2_slots;  // two per batch step: l2err (bit pattern of a non-negative double), negative flag
   int batch_idx;                 // index of this step in the batch
   int prev_checked;              // step batch_idx-1 was a checked step of this batch
   int prev_may_stop;             // ... and its global t-1 > 2
@@ -123,7 +123,7 @@ struct MPArgs {
   double* vacf_slots;   // 3 per batch step
   int batch_idx;
   int accumulate;       // add into the slot instead of overwriting (later launch of a split step)
-  int check_prev;       // evaluate the convergence criterion on slot batch_idx-1
+  int check_slot;       // evaluate the convergence criterion on this (complete, global) slot, or -1
   double lim;           // 1/(2 lx ly lz / Db)
   Ctrl* ctrl;
 };

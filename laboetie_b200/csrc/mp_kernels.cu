@@ -147,8 +147,8 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
   __shared__ int s_flag;
   if (threadIdx.x == 0) {
     int stop = *(volatile int*)&a.ctrl->stop;
-    if (!stop && a.check_prev) {
-      const volatile double* v = a.vacf_slots + 3 * (a.batch_idx - 1);
+    if (!stop && a.check_slot >= 0) {
+      const volatile double* v = a.vacf_slots + 3 * a.check_slot;
       const double ax = fabs(v[0]), ay = fabs(v[1]), az = fabs(v[2]);
       if (ax < a.lim && ay < a.lim && az < a.lim && ax < 1.e-12 && ay < 1.e-12 && az < 1.e-12) {  // :284
         a.ctrl->stop = 1;

@@ -33,7 +33,23 @@ GEOMS = [
     ("cyl11x11x4", lambda: O.geometry(2, 11, 11, 4)),
     ("bcc12", lambda: O.geometry(3, 12, 12, 12)),
     ("bulk5x4x3", lambda: O.geometry(-1, 5, 4, 3)),
+    ("onefluid3x3x3", lambda: _one_fluid()),
+    ("solidplane6x5x8", lambda: _solid_plane()),
+    ("rand40x9x6", lambda: random_nature(40, 9, 6, 0.6, 9)),
 ]
+
+
+def _one_fluid():
+    nat = np.ones((3, 3, 3), np.int8)
+    nat[1, 1, 1] = 0
+    return nat
+
+
+def _solid_plane():
+    nat = random_nature(6, 5, 8, 0.2, 12)
+    nat[3] = 1          # a whole z-plane of solid
+    nat[:, 2, :] = 1    # and a whole y-row slab
+    return nat
 
 
 @pytest.mark.parametrize("name,mk", GEOMS, ids=[g[0] for g in GEOMS])
