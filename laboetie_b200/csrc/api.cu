@@ -80,6 +80,20 @@ struct Force {
 
 enum Phase { PH_CREATED = 0, PH_LB = 1, PH_MP = 2 };
 
+// Strip order for the propagate kernel: segments (strip s, plane p) of consecutive fids, strip-major.
+struct SegTable {
+  int nseg = 0, ntiles = 0;
+  int* tile_cum = nullptr;
+  long long* seg_begin = nullptr;
+  long long* seg_end = nullptr;
+  void release() {
+    cudaFree(tile_cum);
+    cudaFree(seg_begin);
+    cudaFree(seg_end);
+    *this = SegTable();
+  }
+};
+
 }  // namespace
 
 struct lbg_handle_s {
@@ -145,6 +159,7 @@ struct lbg_handle_s {
   double* s = nullptr;
   double* P[2] = {nullptr, nullptr};
   double* A[2] = {nullptr, nullptr};
+  SegTable strips;  // over the planes one propagate launch covers (all own planes, or the interior ones)
 };
 
 namespace {
@@ -384,6 +399,62 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   h->grid_lb = occupancy_grid_lb(h->sm_count, h->lb_minb);
 #undef CKB
   *out = h;
+  return LBG_OK;
+}
+
+// Cut planes [p_lo, p_hi] into strips of rows such that one (strip, plane) segment streams about 16 MB;
+// returns nseg == 0 when a plane is small enough for plain order to keep its neighbours in L2 anyway.
+int build_strips(lbg_handle h, int p_lo, int p_hi, SegTable* t) {
+  t->release();
+  const Geo& g = h->geo;
+  const int np = p_hi - p_lo + 1;
+  if (np < 3) return LBG_OK;
+  const double phi = h->nown > 0 ? (double)h->n_fluid / (double)h->nown : 1.0;
+  // Measured (profiles/variants_r1q.txt): plain fid order is faster on every workload so far -- the
+  // three planes already survive in the 126 MB L2 -- so strips are opt-in (LBG_MP_STRIP_ROWS=<rows>).
+  (void)phi;
+  double rows_d = 0;
+  if (const char* e = std::getenv("LBG_MP_STRIP_ROWS")) rows_d = std::atof(e);
+  if (rows_d <= 0 || rows_d >= g.ly) return LBG_OK;
+  if (rows_d < 2) rows_d = 2;
+  const int rows = (int)rows_d;
+  const int nstrips = (g.ly + rows - 1) / rows;
+  if (nstrips < 2) return LBG_OK;
+  std::vector<long long> idx((size_t)(nstrips + 1) * np), fids(idx.size());
+  for (int s = 0; s <= nstrips; ++s)
+    for (int p = 0; p < np; ++p) {
+      const long long y = (long long)s * rows < g.ly ? (long long)s * rows : g.ly;
+      idx[(size_t)s * np + p] = (long long)(p_lo + p) * g.plane + y * g.lx;
+    }
+  long long *d_idx = nullptr, *d_out = nullptr;
+  CK(cudaMalloc(&d_idx, idx.size() * sizeof(long long)));
+  CK(cudaMalloc(&d_out, idx.size() * sizeof(long long)));
+  CK(cudaMemcpyAsync(d_idx, idx.data(), idx.size() * sizeof(long long), cudaMemcpyHostToDevice, h->st));
+  h->launches += launch_rank_at(g, d_idx, (int)idx.size(), (long long)g.plane * (g.nzl + 2), h->nf, d_out, h->st);
+  CK(cudaMemcpyAsync(fids.data(), d_out, idx.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  cudaFree(d_idx);
+  cudaFree(d_out);
+  std::vector<int> cum(1, 0);
+  std::vector<long long> sb, se;
+  for (int s = 0; s < nstrips; ++s)
+    for (int p = 0; p < np; ++p) {
+      const long long b = fids[(size_t)s * np + p], e = fids[(size_t)(s + 1) * np + p];
+      if (e <= b) continue;
+      sb.push_back(b);
+      se.push_back(e);
+      cum.push_back(cum.back() + (int)((e - b + BLOCK - 1) / BLOCK));
+    }
+  if (sb.empty()) return LBG_OK;
+  CK(cudaMalloc(&t->tile_cum, cum.size() * sizeof(int)));
+  CK(cudaMalloc(&t->seg_begin, sb.size() * sizeof(long long)));
+  CK(cudaMalloc(&t->seg_end, se.size() * sizeof(long long)));
+  CK(cudaMemcpyAsync(t->tile_cum, cum.data(), cum.size() * sizeof(int), cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemcpyAsync(t->seg_begin, sb.data(), sb.size() * sizeof(long long), cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemcpyAsync(t->seg_end, se.data(), se.size() * sizeof(long long), cudaMemcpyHostToDevice, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  t->nseg = (int)sb.size();
+  t->ntiles = cum.back();
   return LBG_OK;
 }
 
@@ -699,6 +770,7 @@ int lbg_destroy(lbg_handle h) {
   cudaFree(h->counts);
   cudaFree(h->fcur.field);
   cudaFree(h->fprev.field);
+  h->strips.release();
   cudaFreeHost(h->h_l2);
   cudaFreeHost(h->h_vacf);
   cudaFreeHost(h->h_ctrl);
@@ -1109,6 +1181,9 @@ int lbg_mp_init(lbg_handle h, double Db, double ka, double kd, const double f_ex
   }
   if (vacf0)
     for (int d = 0; d < 3; ++d) vacf0[d] = v0[d];
+  // strip order over the planes the big propagate launch covers
+  if (h->nranks == 1) RET(build_strips(h, 1, g.nzl, &h->strips));
+  else RET(build_strips(h, 2, g.nzl - 1, &h->strips));
   h->mp_bad = bad;
   h->phase = PH_MP;
   h->it = 0;
@@ -1165,20 +1240,28 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
       a.lim = lim;
       a.ctrl = h->ctrl;
       RET(wait_halo(h));
-      auto launch = [&](long long b, long long e) {
+      auto launch = [&](long long b, long long e, bool use_strips = false) {
         a.fid_begin = b;
         a.fid_end = e;
+        a.nseg = 0;
+        if (use_strips && h->strips.nseg > 0) {
+          a.nseg = h->strips.nseg;
+          a.ntiles = h->strips.ntiles;
+          a.tile_cum = h->strips.tile_cum;
+          a.seg_begin = h->strips.seg_begin;
+          a.seg_end = h->strips.seg_end;
+        }
         h->launches += launch_mp_step(a, h->grid_mp, h->st);
       };
       if (h->nranks == 1) {
-        launch(own_begin(h), own_end(h));
+        launch(own_begin(h), own_end(h), true);
       } else {
         const int all3[3] = {0, 1, 2};
         if (i >= 2) CK(cudaStreamWaitEvent(h->st, h->ev_ar[i & 1], 0));  // all-reduce of step i-2
         launch(ps[1], ps[2]);
         if (nz > 1) launch(ps[nz], ps[nz + 1]);
         RET(halo_exchange(h, h->P[1 - pc], all3, 3, all3, 3));
-        if (nz > 2) launch(ps[2], ps[nz]);
+        if (nz > 2) launch(ps[2], ps[nz], true);
         // all-reduce of this step's vacf on the communication stream, not waited for here
         CK(cudaEventRecord(h->ev_ready, h->st));
         CK(cudaStreamWaitEvent(h->st_comm, h->ev_ready, 0));

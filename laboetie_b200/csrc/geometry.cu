@@ -111,6 +111,21 @@ __global__ void __launch_bounds__(BLOCK) build_gidx_kernel(Geo geo, long long nd
   }
 }
 
+// number of fluid nodes before dense node idx[i] (idx[i] == ndense allowed)
+__global__ void __launch_bounds__(BLOCK) rank_at_kernel(Geo geo, const long long* __restrict__ idx, int n, long long ndense,
+                                                        long long total, long long* __restrict__ out) {
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n) return;
+  const long long g = idx[i];
+  if (g >= ndense) {
+    out[i] = total;
+    return;
+  }
+  const uint2 w = geo.words[g >> 5];
+  const unsigned bit = (unsigned)(g & 31);
+  out[i] = (long long)w.y + __popc(w.x & ((1u << bit) - 1u));
+}
+
 __global__ void __launch_bounds__(BLOCK) count_interfacial_kernel(Geo geo, long long fid_begin, long long fid_end,
                                                                   unsigned long long* count) {
   unsigned int n = 0;
@@ -191,6 +206,12 @@ int launch_build_gidx(const Geo& g, long long nwords, uint32_t* gidx, cudaStream
   const long long ndense = (long long)g.plane * (g.nzl + 2);
   (void)nwords;
   build_gidx_kernel<<<big_grid(ndense), BLOCK, 0, st>>>(g, ndense, gidx);
+  return 1;
+}
+
+int launch_rank_at(const Geo& g, const long long* dense_idx, int n, long long ndense, long long total, long long* out,
+                   cudaStream_t st) {
+  rank_at_kernel<<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(g, dense_idx, n, ndense, total, out);
   return 1;
 }
 

@@ -126,6 +126,11 @@ struct MPArgs {
   int check_slot;       // evaluate the convergence criterion on this (complete, global) slot, or -1
   double lim;           // 1/(2 lx ly lz / Db)
   Ctrl* ctrl;
+  // optional strip order (see SegTable): nseg == 0 means plain fid order over [fid_begin, fid_end)
+  int nseg, ntiles;
+  const int* tile_cum;          // nseg + 1: tiles before segment k
+  const long long* seg_begin;   // nseg: first fid of segment k
+  const long long* seg_end;     // nseg: one past the last fid of segment k
 };
 
 struct ProfileArgs {
@@ -140,6 +145,8 @@ struct ProfileArgs {
 int launch_build_bits(int plane, int nzl, const int8_t* nature_halo, uint2* words, long long nwords, cudaStream_t st);
 int launch_scan_ranks(uint2* words, long long nwords, unsigned long long* total, cudaStream_t st);
 int launch_build_gidx(const Geo& g, long long nwords, uint32_t* gidx, cudaStream_t st);
+int launch_rank_at(const Geo& g, const long long* dense_idx, int n, long long ndense, long long total, long long* out,
+                   cudaStream_t st);
 int launch_count_interfacial(const Geo& g, long long fid_begin, long long fid_end, unsigned long long* count,
                              cudaStream_t st);
 int launch_dense_interfacial(const Geo& g, int8_t* out_own, cudaStream_t st);

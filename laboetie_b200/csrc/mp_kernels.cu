@@ -164,12 +164,30 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
   const Geo& geo = a.geo;
   const long long nfa = geo.nfa;
   double vx = 0, vy = 0, vz = 0;
-  const long long first = a.fid_begin + (long long)blockIdx.x * BLOCK + threadIdx.x;
-  const long long stride = (long long)gridDim.x * BLOCK;
-  uint32_t gi_next = first < a.fid_end ? __ldg(geo.gidx + first) : 0u;
-  for (long long ff = first; ff < a.fid_end; ff += stride) {
+  // Tile order.  Plain: tiles of BLOCK consecutive fids.  Strip order (nseg > 0): the own planes are cut
+  // into strips of rows and all planes of a strip are visited before the next strip, so the three
+  // planes a node gathers P from were touched a few MB of traffic ago and are still in L2: P is then
+  // read from HBM once per step instead of up to three times.
+  const int ntiles = a.nseg > 0 ? a.ntiles : (int)((a.fid_end - a.fid_begin + BLOCK - 1) / BLOCK);
+  int seg = 0;
+  auto node_of = [&](int tile, int& k) -> long long {  // fid of this thread in `tile`, or -1
+    if (a.nseg == 0) {
+      const long long f = a.fid_begin + (long long)tile * BLOCK + threadIdx.x;
+      return f < a.fid_end ? f : -1;
+    }
+    while (tile >= a.tile_cum[k + 1]) ++k;  // tiles are visited in increasing order
+    const long long f = a.seg_begin[k] + (long long)(tile - a.tile_cum[k]) * BLOCK + threadIdx.x;
+    return f < a.seg_end[k] ? f : -1;
+  };
+  long long f_next = blockIdx.x < ntiles ? node_of(blockIdx.x, seg) : -1;
+  uint32_t gi_next = f_next >= 0 ? __ldg(geo.gidx + f_next) : 0u;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long ff = f_next;
     const uint32_t gi = gi_next;
-    if (ff + stride < a.fid_end) gi_next = __ldg(geo.gidx + ff + stride);
+    const int tn = tile + gridDim.x;
+    f_next = tn < ntiles ? node_of(tn, seg) : -1;
+    if (f_next >= 0) gi_next = __ldg(geo.gidx + f_next);
+    if (ff < 0) continue;
     const int fid = (int)ff;
     const int g = (int)(gi & GIDX_MASK);
     const bool adsorbing = a.ads && (gi & GIDX_INTERFACIAL);
@@ -273,6 +291,11 @@ int launch_mp_init(const MPInitArgs& a, int grid, cudaStream_t st) {
 }
 
 int launch_mp_step(const MPArgs& a, int grid, cudaStream_t st) {
+  if (a.nseg > 0) {
+    if (a.ntiles <= 0) return 0;
+    mp_step_kernel<<<a.ntiles < grid ? a.ntiles : grid, BLOCK, 0, st>>>(a);
+    return 1;
+  }
   if (a.fid_end <= a.fid_begin) return 0;
   mp_step_kernel<<<clamp_grid(a.fid_end - a.fid_begin, grid), BLOCK, 0, st>>>(a);
   return 1;

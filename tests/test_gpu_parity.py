@@ -234,6 +234,31 @@ def test_moment_propagation_bit_exact(name, mk, ka, kd):
         assert (np.abs(v - ref_v) <= RTOL * scale).all()
 
 
+@pytest.mark.parametrize("rows", ["2", "3", "5"])
+def test_moment_propagation_strip_order(rows, monkeypatch):
+    """The L2-friendly strip order of the propagate kernel (forced on a small lattice) changes nothing per node."""
+    lb = _gpu()
+    monkeypatch.setenv("LBG_MP_STRIP_ROWS", rows)
+    nat = random_nature(9, 11, 7, 0.3, 51)
+    itf = O.detect_interfacial(nat)
+    f = [1e-4, 2e-4, -1e-4]
+    st = O.LBState(nat)
+    st.set_force_uniform(f)
+    for _ in range(10):
+        st.step()
+    mp = O.MPState(nat, itf, st.rho, st.jx, st.jy, st.jz, f, 0.01, 0.1, 0.01)
+    ref_v = np.array([mp.propagate()[1] for _ in range(15)])
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_init(1.0)
+        sim.lb_set_force_uniform(f)
+        sim.lb_step(10, check_every=0)
+        sim.mp_init(0.01, 0.1, 0.01, f)
+        done, conv, v = sim.mp_step(15)
+        P, A = sim.mp_download()
+        assert np.array_equal(P, mp.P[0]) and np.array_equal(A, mp.Pads[0])
+        assert (np.abs(v - ref_v) <= RTOL * np.abs(mp.vacf0).max()).all()
+
+
 def test_mp_convergence_step_matches():
     """Bulk fluid at rest: vacf(t>=1) = 0, so propagate reports convergence at it=3 (it>2, :284)."""
     lb = _gpu()
