@@ -41,6 +41,80 @@ def equilibration(sim: LaboetieGPU, f_ext, tau=1.0, target_error=1e-10, rho0=1.0
     return dict(rc=2, t_exit=t, t_fext=t_fext, l2err=np.concatenate(hist) if hist else np.zeros(0))
 
 
+def compensating_force_field(nature, f_ext, particle_diameter=1, particle_coordinates=None, geometry_label=0):
+    """The `compensate_f_ext` force field of equilibration.f90:388-487 (host side, as in the reference's
+    driver): f_ext spread over the lattice points of a spherical particle of odd diameter, compensated by a
+    uniform background in the bulk cell (geometryLabel = -1).  nature: int8 (lz, ly, lx).
+    Returns (fx, fy, fz, nodes_in_particle)."""
+    nature = np.asarray(nature)
+    lz, ly, lx = nature.shape
+    pd = int(particle_diameter)
+    if pd % 2 == 0:
+        raise ValueError("particle diameter must be odd")                                   # :391-395
+    if lx % 2 == 0 or ly % 2 == 0 or lz % 2 == 0:
+        raise ValueError("when compensate_f_ext, there should be odd number of nodes in all directions")   # :397-402
+    px, py, pz = particle_coordinates or (lx // 2 + 1, ly // 2 + 1, lz // 2 + 1)            # :414 (1-based)
+    pdr = pd // 2
+    fluid = nature == 0
+    inside = np.zeros(nature.shape, bool)
+    for i in range(px - pdr, px + pdr + 1):                                                   # :419-432
+        for j in range(py - pdr, py + pdr + 1):
+            for k in range(pz - pdr, pz + pdr + 1):
+                if (i - px) ** 2 + (j - py) ** 2 + (k - pz) ** 2 > (pd / 2.0) ** 2:
+                    continue
+                if not fluid[k - 1, j - 1, i - 1]:
+                    raise ValueError("Dominika's particle at a solid node")                  # :435-438
+                inside[k - 1, j - 1, i - 1] = True
+    l = int(inside.sum())
+    nfl = int(fluid.sum())
+    out = []
+    for d in range(3):
+        f = np.where(inside, float(f_ext[d]), 0.0)
+        # the reference recognises particle nodes by comparing all three components with f_ext (:450,468)
+        out.append(f)
+    match = (out[0] == f_ext[0]) & (out[1] == f_ext[1]) & (out[2] == f_ext[2])
+    res = []
+    for d in range(3):
+        if geometry_label == -1:                                                              # :449-458
+            f = np.where(match, -float(f_ext[d]) / nfl + out[d] / l, -float(f_ext[d]) / nfl)
+        else:                                                                                 # :467-477
+            f = np.where(match, out[d] / l, 0.0)
+        res.append(np.where(fluid, f, 0.0))                                                   # :480-484
+    return res[0], res[1], res[2], l
+
+
+def equilibration_compensated(sim: LaboetieGPU, nature, f_ext, tau=1.0, target_error=1e-10, rho0=1.0,
+                              particle_diameter=1, particle_coordinates=None, geometry_label=0, max_steps=10**9):
+    """Phase A with compensate_f_ext = T (equilibration.f90:185-188,388-487): as `equilibration`, but the
+    force switched on at the first convergence is the particle + background field, and the momentum at the
+    particle centre is recorded at the start of every later step (output/v_centralnode.dat, :187)."""
+    lz, ly, lx = np.asarray(nature).shape
+    px, py, pz = particle_coordinates or (lx // 2 + 1, ly // 2 + 1, lz // 2 + 1)
+    sim.lb_init(rho0)
+    hist, probe = [], []
+    without_fext, t, t_fext = False, 0, 0
+    while t < max_steps:
+        if without_fext:
+            probe.append((t + 1 - t_fext,) + tuple(sim.lb_probe(px - 1, py - 1, pz - 1)[:3]))
+            n = 1                                # v_centralnode.dat wants the probe before every step
+        else:
+            n = min(4096, max_steps - t)
+        done, conv, h = sim.lb_step(n, tau=tau, check_every=1, target_error=target_error)
+        hist.append(h)
+        t += done
+        if not conv:
+            continue
+        if not without_fext:
+            without_fext = True
+            t_fext = t + 1
+            fx, fy, fz, _ = compensating_force_field(nature, f_ext, particle_diameter, particle_coordinates,
+                                                     geometry_label)
+            sim.lb_set_force_field(fx, fy, fz)
+        else:
+            return dict(rc=0, t_exit=t, t_fext=t_fext, l2err=np.concatenate(hist), v_centralnode=np.array(probe))
+    return dict(rc=2, t_exit=t, t_fext=t_fext, l2err=np.concatenate(hist), v_centralnode=np.array(probe))
+
+
 def drop_tracers(sim: LaboetieGPU, f_ext, Db, ka, kd, max_steps, chunk=4096):
     """Phase B, drop_tracers.f90:20-55.  max_steps < 0 means run until converged (:40).
 

@@ -197,7 +197,7 @@ int main(int argc, char** argv) {
   const double eps = 2.220446049250313e-16;
   if (std::fabs(in.dp("sigma", 0.0)) > eps) stop("ERROR: laboetie can only consider uncharged systems.");  // equilibration.f90:28-33
   if (in.logical("first_order_only", false)) stop("first_order_only = T is not supported (undefined behaviour in the reference, module_collision.f90:110-125)");
-  if (in.logical("compensate_f_ext", false)) stop("compensate_f_ext is not mirrored by this driver yet (use lbg_lb_set_force_field)");
+  const bool compensate = in.logical("compensate_f_ext", false);
   const double tau = in.dp("relaxation_time", 1.0);
   const double target_error = in.dp("target_error", 1.e-10);
   const double rho0 = in.dp("initialSolventDensity", 1.0);
@@ -246,6 +246,13 @@ int main(int argc, char** argv) {
   FILE* tmf = write_total_mass_flux ? open("total_mass_flux.dat") : nullptr;
   if (!quiet) std::printf("\n Lattice Boltzmann\n =================\n        step\n        ----\n");
 
+  // compensate_f_ext (equilibration.f90:123-124,185-188,388-487): particle centre and probe file
+  int pcx = lx / 2 + 1, pcy = ly / 2 + 1, pcz = lz / 2 + 1;
+  if (in.has("particle_coordinates")) {
+    std::istringstream ss(in.kv["particle_coordinates"]);
+    ss >> pcx >> pcy >> pcz;
+  }
+  FILE* vcn = compensate ? open("v_centralnode.dat") : nullptr;
   bool without_fext = false;
   long t = 0, tfext = 0;
   std::vector<double> hist(4096);
@@ -254,6 +261,12 @@ int main(int argc, char** argv) {
   const bool every_step_io = write_total_mass_flux;
   for (;;) {
     long chunk = every_step_io ? 1 : 4096;
+    if (compensate && without_fext) {  // :185-188: momentum at the particle centre before every step
+      double pr[4];
+      ck(lbg_lb_probe(h, pcx - 1, pcy - 1, pcz - 1, pr), h, "equilibration (v_centralnode)");
+      std::fprintf(vcn, "%12ld %24.16E %24.16E %24.16E\n", t + 1 - tfext, pr[0], pr[1], pr[2]);
+      chunk = 1;
+    }
     const long next_write = (t / print_files_frequency + 1) * print_files_frequency;  // smallest multiple > t
     const bool write_now = (t + 1 == next_write) || (t + 1 == 1);
     if (write_now) {
@@ -280,7 +293,49 @@ int main(int argc, char** argv) {
     if (!without_fext) {  // :377-386
       without_fext = true;
       tfext = t + 1;
-      ck(lbg_lb_set_force_uniform(h, f_ext), h, "equilibration (f_ext)");
+      if (!compensate) {
+        ck(lbg_lb_set_force_uniform(h, f_ext), h, "equilibration (f_ext)");
+      } else {  // :388-487
+        const int pd = (int)in.integer("dominika_particle_diameter", 1);
+        if (pd % 2 == 0) stop("ERROR: l. 285 particle diameter must be odd");
+        if (lx % 2 == 0 || ly % 2 == 0 || lz % 2 == 0)
+          stop("ERROR: when compensate_f_ext, there should be odd number of nodes in all directions");
+        const int pdr = pd / 2;
+        const size_t N = nature.size();
+        std::vector<double> fx(N, 0.0), fy(N, 0.0), fz(N, 0.0);
+        std::vector<char> part(N, 0);
+        long l = 0, fluid_nodes = 0;
+        for (int8_t v : nature) fluid_nodes += (v == 0);
+        for (int i = pcx - pdr; i <= pcx + pdr; ++i)
+          for (int j = pcy - pdr; j <= pcy + pdr; ++j)
+            for (int k = pcz - pdr; k <= pcz + pdr; ++k) {
+              const long d2 = (long)(i - pcx) * (i - pcx) + (long)(j - pcy) * (j - pcy) + (long)(k - pcz) * (k - pcz);
+              if (4 * d2 > (long)pd * pd) continue;  // norm2 > pd/2
+              if (i < 1 || j < 1 || k < 1 || i > lx || j > ly || k > lz) stop("particle outside the lattice");
+              const size_t r = (size_t)(i - 1) + (size_t)lx * ((size_t)(j - 1) + (size_t)ly * (k - 1));
+              if (nature[r] != 0) stop("ERROR: l306 of equilibration.f90. Dominika's particle at a solid node");
+              fx[r] = f_ext[0];
+              fy[r] = f_ext[1];
+              fz[r] = f_ext[2];
+              ++l;
+            }
+        for (size_t r = 0; r < N; ++r) {
+          // the reference recognises particle nodes by comparing the three components with f_ext (:450,468)
+          const bool match = fx[r] == f_ext[0] && fy[r] == f_ext[1] && fz[r] == f_ext[2];
+          if (label == -1) {
+            fx[r] = -f_ext[0] / (double)fluid_nodes + (match ? fx[r] / (double)l : 0.0);
+            fy[r] = -f_ext[1] / (double)fluid_nodes + (match ? fy[r] / (double)l : 0.0);
+            fz[r] = -f_ext[2] / (double)fluid_nodes + (match ? fz[r] / (double)l : 0.0);
+          } else {
+            fx[r] = match ? fx[r] / (double)l : 0.0;
+            fy[r] = match ? fy[r] / (double)l : 0.0;
+            fz[r] = match ? fz[r] / (double)l : 0.0;
+          }
+          if (nature[r] != 0) fx[r] = fy[r] = fz[r] = 0.0;
+        }
+        if (!quiet) std::printf("        Dominika's particle has diameter (lb units) %d, %ld nodes\n", pd, l);
+        ck(lbg_lb_set_force_field(h, fx.data(), fy.data(), fz.data()), h, "equilibration (compensate_f_ext)");
+      }
     } else {
       break;  // :373-374
     }
@@ -289,6 +344,7 @@ int main(int argc, char** argv) {
   write_profiles(h, lx, ly, lz, fz, fy, fx, dz, dy, dx);
   for (FILE* f : {fz, fy, fx, dz, dy, dx, l2f}) std::fclose(f);
   if (tmf) std::fclose(tmf);
+  if (vcn) std::fclose(vcn);
   {  // equilibration.f90:527-533
     std::vector<double> rho((size_t)lx * ly * lz), jx(rho.size()), jy(rho.size()), jz(rho.size());
     ck(lbg_lb_download_moments(h, rho.data(), jx.data(), jy.data(), jz.data()), h, "equilibration (write-back)");

@@ -459,6 +459,72 @@ int orc_equilibration(int lx, int ly, int lz, const int8_t* nature, double tau, 
   return 2;
 }
 
+// equilibration.f90:388-487: the `compensate_f_ext` force field ("Dominika particle").  A particle of
+// odd diameter pd centred on (px,py,pz) (1-based) carries the force f_ext, spread evenly over its l nodes;
+// in the bulk cell (geometryLabel == -1) a uniform background -f_ext/fluid_nodes compensates it.
+// Returns 0, or <0 for the reference's stops (-1 even diameter, -2 even lattice extent, -3 particle on a
+// solid node, -4 compensation check failed).  *nodes_in_particle receives l.
+int orc_compensate_force(int lx, int ly, int lz, const int8_t* nature, const double* f_ext, int pd, int px, int py,
+                         int pz, int geometry_label, double* fx, double* fy, double* fz, int* nodes_in_particle) {
+  const Dim d{lx, ly, lz};
+  const size_t N = d.N();
+  if (pd % 2 == 0) return -1;                                 // :391-395
+  if (lx % 2 == 0 || ly % 2 == 0 || lz % 2 == 0) return -2;   // :397-402
+  const int pdr = pd / 2;                                     // :403
+  long fluid_nodes = 0;
+  for (size_t r = 0; r < N; ++r) fluid_nodes += (nature[r] == FLUID);
+  for (size_t r = 0; r < N; ++r) fx[r] = fy[r] = fz[r] = 0.0;  // :405-407
+  int l = 0;
+  bool err = false;
+  for (int i = px - pdr; i <= px + pdr; ++i)                   // :419-432
+    for (int j = py - pdr; j <= py + pdr; ++j)
+      for (int k = pz - pdr; k <= pz + pdr; ++k) {
+        const double v[3] = {(double)(i - px), (double)(j - py), (double)(k - pz)};
+        if (norm2_gfortran(v, 3) > (double)pd / 2.0) continue;
+        const size_t r = d.at(i, j, k);
+        if (nature[r] != FLUID) err = true;
+        fx[r] = f_ext[0];
+        fy[r] = f_ext[1];
+        fz[r] = f_ext[2];
+        ++l;
+      }
+  *nodes_in_particle = l;
+  if (err) return -3;                                          // :435-438
+  if (geometry_label == -1) {                                  // :449-466
+    for (size_t r = 0; r < N; ++r) {
+      if (fx[r] == f_ext[0] && fy[r] == f_ext[1] && fz[r] == f_ext[2]) {
+        fx[r] = -f_ext[0] / (double)fluid_nodes + fx[r] / (double)l;
+        fy[r] = -f_ext[1] / (double)fluid_nodes + fy[r] / (double)l;
+        fz[r] = -f_ext[2] / (double)fluid_nodes + fz[r] / (double)l;
+      } else {
+        fx[r] = -f_ext[0] / (double)fluid_nodes;
+        fy[r] = -f_ext[1] / (double)fluid_nodes;
+        fz[r] = -f_ext[2] / (double)fluid_nodes;
+      }
+    }
+    double sx = 0, sy = 0, sz = 0;
+    for (size_t r = 0; r < N; ++r) {
+      sx += fx[r];
+      sy += fy[r];
+      sz += fz[r];
+    }
+    if (std::fabs(sx / fluid_nodes) > EPS || std::fabs(sy / fluid_nodes) > EPS || std::fabs(sz / fluid_nodes) > EPS) return -4;
+  } else {                                                     // :467-477
+    for (size_t r = 0; r < N; ++r) {
+      if (fx[r] == f_ext[0] && fy[r] == f_ext[1] && fz[r] == f_ext[2]) {
+        fx[r] = fx[r] / (double)l;
+        fy[r] = fy[r] / (double)l;
+        fz[r] = fz[r] / (double)l;
+      } else {
+        fx[r] = fy[r] = fz[r] = 0.0;
+      }
+    }
+  }
+  for (size_t r = 0; r < N; ++r)                               // :480-484
+    if (nature[r] != FLUID) fx[r] = fy[r] = fz[r] = 0.0;
+  return 0;
+}
+
 // equilibration.f90:161-172,505-516: one row of 4 per index along `axis`
 // (0=x,1=y,2=z): SUM(jx), SUM(jy), SUM(jz), SUM(density)/MAX(COUNT(density>eps),1).
 void orc_profiles(int lx, int ly, int lz, const double* density, const double* jx, const double* jy, const double* jz,

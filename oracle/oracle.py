@@ -57,6 +57,7 @@ def lib():
         L.orc_moments.argtypes = dims + [f64p] * 11 + [C.POINTER(D)]
         L.orc_lb_step.argtypes = dims + [i8p, D] + [f64p] * 11 + [C.POINTER(D)]
         L.orc_equilibration.argtypes = dims + [i8p, D, D, f64p, I] + [f64p] * 5 + [f64p, I, C.POINTER(I), C.POINTER(I)]
+        L.orc_compensate_force.argtypes = dims + [i8p, f64p, I, I, I, I, I, f64p, f64p, f64p, C.POINTER(I)]
         L.orc_profiles.argtypes = dims + [f64p] * 4 + [I, f64p]
         L.orc_profiles.restype = None
         L.orc_total_flux.argtypes = dims + [f64p] * 3 + [f64p]
@@ -157,6 +158,20 @@ def equilibration(nature, f_ext, tau=1.0, target_error=1e-10, rho0=1.0, max_step
                                  n, rho, jx, jy, jz, hist, hist_cap, C.byref(te), C.byref(tf))
     return dict(rc=rc, n=n, rho=rho, jx=jx, jy=jy, jz=jz, t_exit=te.value, t_fext=tf.value,
                 l2err=hist[: min(te.value, hist_cap)].copy())
+
+
+def compensate_force(nature, f_ext, pd=1, centre=None, geometry_label=0):
+    """equilibration.f90:388-487; centre is 1-based (px,py,pz), default (n/2+1) as the reference."""
+    lx, ly, lz = _dims(nature)
+    if centre is None:
+        centre = (lx // 2 + 1, ly // 2 + 1, lz // 2 + 1)
+    fx, fy, fz = (np.zeros(nature.shape) for _ in range(3))
+    l = C.c_int()
+    rc = lib().orc_compensate_force(lx, ly, lz, nature, np.asarray(f_ext, np.float64), pd, *centre, geometry_label,
+                                    fx, fy, fz, C.byref(l))
+    if rc:
+        raise ValueError(f"orc_compensate_force -> {rc}")
+    return fx, fy, fz, l.value
 
 
 def profiles(rho, jx, jy, jz, axis):

@@ -68,3 +68,23 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".f90", "Makefile")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert not bad.search(txt), os.path.join(dp, f)
+
+
+def test_compensating_force_field_matches_oracle():
+    """Host-side mirror of equilibration.f90:388-487 against the oracle restatement."""
+    from laboetie_b200 import driver
+    from oracle import oracle as O
+    for label, shape, pd in ((-1, (7, 5, 9), 3), (1, (5, 7, 9), 3), (-1, (5, 5, 5), 1), (1, (9, 9, 11), 5)):
+        nat = O.geometry(label, *shape)
+        f = [1e-3, -2e-3, 5e-4]
+        a = O.compensate_force(nat, f, pd=pd, geometry_label=label)
+        b = driver.compensating_force_field(nat, f, pd, None, label)
+        assert a[3] == b[3]
+        for x, y in zip(a[:3], b[:3]):
+            assert np.array_equal(x, y)
+        if label == -1:
+            assert abs(a[0].sum()) < 1e-15
+    with pytest.raises(ValueError):
+        driver.compensating_force_field(O.geometry(-1, 4, 5, 5), [1, 0, 0], 1)
+    with pytest.raises(ValueError):
+        driver.compensating_force_field(O.geometry(-1, 5, 5, 5), [1, 0, 0], 2)

@@ -68,3 +68,24 @@ def test_driver_runs_config1_end_to_end(tmp_path):
     prof = [l for l in open(tmp_path / "output" / "mass-flux_profile_along_z.dat") if not l.startswith("#") and l.strip()]
     last = np.array([[float(x) for x in l.split()] for l in prof[-50:]])
     assert np.allclose(last[:, 1:], g["prof_z"][:, :3], rtol=1e-12, atol=1e-300)
+
+
+@pytest.mark.gpu
+def test_driver_compensate_f_ext(tmp_path):
+    """compensate_f_ext = T through the compiled driver against the Python mirror (same C ABI underneath)."""
+    _build()
+    import laboetie_b200 as lb
+    from laboetie_b200 import driver
+    from oracle import oracle as O
+    (tmp_path / "lb.in").write_text(
+        "lx = 7\nly = 5\nlz = 9\ngeometryLabel = -1\nf_ext = 1.e-4 0.0 3.e-4\ncompensate_f_ext = T\n"
+        "dominika_particle_diameter = 3\nrelaxation_time = 0.9\ntarget_error = 1.e-9\n")
+    subprocess.run([EXE, "--input", str(tmp_path / "lb.in"), "--outdir", str(tmp_path / "output"), "--quiet"], check=True)
+    nat = O.geometry(-1, 7, 5, 9)
+    with lb.LaboetieGPU(nat) as sim:
+        r = driver.equilibration_compensated(sim, nat, [1e-4, 0, 3e-4], tau=0.9, target_error=1e-9,
+                                             particle_diameter=3, geometry_label=-1)
+    l2 = np.loadtxt(tmp_path / "output" / "l2err.dat")
+    assert l2.shape[0] == r["t_exit"] and np.array_equal(l2[:, 1], r["l2err"])
+    v = np.loadtxt(tmp_path / "output" / "v_centralnode.dat")
+    assert np.array_equal(v, r["v_centralnode"])

@@ -153,6 +153,44 @@ def test_force_field_and_upload_paths():
         assert np.array_equal(jx, st.jx) and np.array_equal(rho, st.rho)
 
 
+@pytest.mark.parametrize("label,shape", [(-1, (7, 5, 9)), (1, (5, 7, 9))])
+def test_compensate_f_ext_workflow(label, shape):
+    """compensate_f_ext = T (equilibration.f90:185-188,388-487): particle force field +
+    background, central-node probe every step, same exit steps as the oracle-driven loop."""
+    lb = _gpu()
+    from laboetie_b200 import driver
+    nat = O.geometry(label, *shape)
+    f = [1e-4, 0.0, 3e-4]
+    tau, target, pd = 0.9, 1e-8, 3
+    # oracle-driven reference loop
+    st = O.LBState(nat, 1.0, tau)
+    px, py, pz = shape[0] // 2 + 1, shape[1] // 2 + 1, shape[2] // 2 + 1
+    hist, probe, without, t, tf = [], [], False, 0, 0
+    while True:
+        if without:
+            probe.append((t + 1 - tf, st.jx[pz - 1, py - 1, px - 1], st.jy[pz - 1, py - 1, px - 1], st.jz[pz - 1, py - 1, px - 1]))
+        rc, e = st.step()
+        assert rc == 0
+        t += 1
+        hist.append(e)
+        if e <= target and t > 2:
+            if not without:
+                without, tf = True, t + 1
+                st.fx, st.fy, st.fz, nl = O.compensate_force(nat, f, pd=pd, geometry_label=label)
+                assert nl == 19
+            else:
+                break
+        assert t < 20000
+    with lb.LaboetieGPU(nat) as sim:
+        r = driver.equilibration_compensated(sim, nat, f, tau=tau, target_error=target, particle_diameter=pd,
+                                             geometry_label=label)
+        assert (r["t_exit"], r["t_fext"]) == (t, tf)
+        assert np.array_equal(r["l2err"], np.array(hist))
+        assert np.array_equal(r["v_centralnode"], np.array(probe))
+        rho, jx, jy, jz = sim.lb_moments()
+        assert np.array_equal(jx, st.jx) and np.array_equal(jz, st.jz) and np.array_equal(rho, st.rho)
+
+
 def test_equilibration_exit_steps_match_reference_semantics():
     """Stock lb.in leaves the loop at t=4; a forced slit reproduces exit step and l2err history."""
     lb = _gpu()
