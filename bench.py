@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--in-place", action="store_true", help="Phase A with the AA pattern (one population buffer)")
     ap.add_argument("--also", default="cfg2,cfg3", help="extra single-GPU workloads reported under 'also' (N=1 only)")
     return ap.parse_args()
 
@@ -227,7 +228,10 @@ def run_ours(args):
 
     def make_sim():
         if nranks == 1:
-            return lb.LaboetieGPU(nat, device=local)
+            sim = lb.LaboetieGPU(nat, device=local)
+            if args.in_place:
+                sim.lb_set_in_place(True)
+            return sim
         sim = lb.LaboetieGPU(nat, device=local, lz_global=lz, k0=k0, slab=True)
         uid = [api.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -339,7 +343,8 @@ def run_ours(args):
         "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "lattice": [lx, ly, lz], "parallelism": f"z-slabs x{nranks}",
                    "fluid_fraction": nf_tot / n_total, "interfacial_fluid_fraction": nif_tot / n_total, "tau": TAU, **TRACER,
-                   "check_every": ce, "l2": "working set >> 126 MB L2; no flush needed",
+                   "check_every": ce, "phase_a_layout": "in-place (AA)" if args.in_place else "two-lattice",
+                   "l2": "working set >> 126 MB L2; no flush needed",
                    "step": "1 LB step + 1 MP step; K LB steps then K MP steps timed"},
         "lb": {"mlups": n_total * K / (t_lb * 1e-3) / 1e6, "mflups": nf_tot * K / (t_lb * 1e-3) / 1e6, "ms_per_step": t_lb / K},
         "mp": {"mlups": n_total * K / (t_mp * 1e-3) / 1e6, "mflups": nf_tot * K / (t_mp * 1e-3) / 1e6, "ms_per_step": t_mp / K},

@@ -13,7 +13,7 @@ module laboetie_gpu
   private
   public :: lbg_create, lbg_create_slab, lbg_destroy, lbg_comm_unique_id, lbg_comm_init, lbg_partition
   public :: lbg_get_interfacial, lbg_get_counts
-  public :: lbg_lb_init, lbg_lb_upload, lbg_lb_set_force_uniform, lbg_lb_set_force_field, lbg_lb_step, lbg_lb_time
+  public :: lbg_lb_set_in_place, lbg_lb_init, lbg_lb_upload, lbg_lb_set_force_uniform, lbg_lb_set_force_field, lbg_lb_step, lbg_lb_time
   public :: lbg_lb_download_moments, lbg_lb_download_populations, lbg_lb_profiles, lbg_lb_total_flux, lbg_lb_probe
   public :: lbg_mp_init, lbg_mp_step, lbg_mp_download, lbg_sync, lbg_status_message
 
@@ -64,6 +64,11 @@ module laboetie_gpu
       import :: c_ptr, c_int, c_int64_t
       type(c_ptr), value :: h
       integer(c_int64_t), intent(out) :: n_fluid, n_interfacial_fluid
+    end function
+    integer(c_int) function lbg_lb_set_in_place(h, on) bind(C, name="lbg_lb_set_in_place")
+      import :: c_ptr, c_int
+      type(c_ptr), value :: h
+      integer(c_int), value :: on
     end function
     integer(c_int) function lbg_lb_init(h, rho0) bind(C, name="lbg_lb_init")
       import :: c_ptr, c_int, c_double

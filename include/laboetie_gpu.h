@@ -99,6 +99,12 @@ int lbg_lb_init(lbg_handle h, double rho0);
  * density / momentum density the next collide will consume. */
 int lbg_lb_upload(lbg_handle h, const double* n, const double* rho, const double* jx, const double* jy,
                   const double* jz);
+/* Memory-lean option (north_star "AA-pattern in place"): with on != 0 Phase A keeps ONE population
+ * buffer (152 instead of 304 bytes per fluid node) and alternates a local and a pull/push kernel.
+ * Results, l2err history and exit step are identical to the default two-lattice mode; the per-step
+ * convergence scalar then costs a separate moments pass on checked steps (504 vs 352 bytes per node).
+ * Call before lbg_lb_init / lbg_lb_upload.  Single-slab handles only. */
+int lbg_lb_set_in_place(lbg_handle h, int on);
 /* equilibration.f90:381-386: the same force on every fluid node, 0 on solid. */
 int lbg_lb_set_force_uniform(lbg_handle h, const double f[3]);
 /* equilibration.f90:388-487 (compensate_f_ext): arbitrary per-node force (own planes). */

@@ -25,7 +25,7 @@ STATUS = {
 SYMBOLS = [
     "lbg_abi_version", "lbg_status_string", "lbg_last_error", "lbg_device_count", "lbg_partition", "lbg_halo_plan",
     "lbg_create", "lbg_create_slab", "lbg_destroy", "lbg_comm_unique_id", "lbg_comm_init", "lbg_get_interfacial",
-    "lbg_get_counts", "lbg_lb_init", "lbg_lb_upload", "lbg_lb_set_force_uniform", "lbg_lb_set_force_field",
+    "lbg_get_counts", "lbg_lb_set_in_place", "lbg_lb_init", "lbg_lb_upload", "lbg_lb_set_force_uniform", "lbg_lb_set_force_field",
     "lbg_lb_step", "lbg_lb_time", "lbg_lb_download_moments", "lbg_lb_download_populations", "lbg_lb_profiles",
     "lbg_lb_total_flux", "lbg_lb_probe", "lbg_mp_init", "lbg_mp_step", "lbg_mp_download", "lbg_timer_start",
     "lbg_timer_stop", "lbg_launch_count", "lbg_sync",
@@ -70,6 +70,7 @@ def load_library():
     L.lbg_comm_init.argtypes = [P, I, I, C.c_char_p]
     L.lbg_get_interfacial.argtypes = [P, i8]
     L.lbg_get_counts.argtypes = [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.lbg_lb_set_in_place.argtypes = [P, I]
     L.lbg_lb_init.argtypes = [P, D]
     L.lbg_lb_upload.argtypes = [P, f64, f64, f64, f64, f64]
     L.lbg_lb_set_force_uniform.argtypes = [P, C.POINTER(D * 3)]
@@ -191,6 +192,10 @@ class LaboetieGPU:
         return a.value, b.value
 
     # -- Phase A ----------------------------------------------------------
+    def lb_set_in_place(self, on=True):
+        """AA pattern: one population buffer; call before lb_init / lb_upload."""
+        self._ck(self._L.lbg_lb_set_in_place(self._h, int(bool(on))))
+
     def lb_init(self, rho0=1.0):
         self._ck(self._L.lbg_lb_init(self._h, rho0))
 

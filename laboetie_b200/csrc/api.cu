@@ -139,6 +139,9 @@ struct lbg_handle_s {
 
   Phase phase = PH_CREATED;
   // Phase A
+  bool in_place = false;     // AA pattern: populations live in f[0] only (lb_aa_kernels.cu)
+  bool aa_swapped = false;   // layout of f[0] in in-place mode: false = N(t), true = S(t)
+  int grid_aa = 148;
   long long t = 0;
   bool precollision = true;  // f[src] holds n(t) (not yet collided) since init/upload
   int src = 0;               // f[src] = n*(t) (or n(t) if precollision); f[1-src] = n*(t+1) when collided_ok
@@ -386,8 +389,7 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
 
   // ---- fields
   const size_t nb = (size_t)h->geo.nfa * sizeof(double);
-  CKB(cudaMalloc(&h->f[0], 19 * nb));
-  CKB(cudaMalloc(&h->f[1], 19 * nb));
+  CKB(cudaMalloc(&h->f[0], 19 * nb));  // f[1] is allocated when a second lattice is first needed
   CKB(cudaMalloc(&h->mom, 4 * nb));
   CKB(cudaMalloc(&h->jpp[0], 3 * nb));
   CKB(cudaMalloc(&h->jpp[1], 3 * nb));
@@ -397,6 +399,7 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   if (const char* e = std::getenv("LBG_LB_MINB")) h->lb_minb = std::atoi(e) >= 3 ? 3 : 2;
   else h->lb_minb = (h->n_fluid < (8LL << 20)) ? 3 : 2;
   h->grid_lb = occupancy_grid_lb(h->sm_count, h->lb_minb);
+  h->grid_aa = occupancy_grid_aa(h->sm_count);
 #undef CKB
   *out = h;
   return LBG_OK;
@@ -455,6 +458,14 @@ int build_strips(lbg_handle h, int p_lo, int p_hi, SegTable* t) {
   CK(cudaStreamSynchronize(h->st));
   t->nseg = (int)sb.size();
   t->ntiles = cum.back();
+  return LBG_OK;
+}
+
+int ensure_second_lattice(lbg_handle h) {
+  if (!h->f[1]) {
+    CK(cudaMalloc(&h->f[1], 19 * (size_t)h->geo.nfa * sizeof(double)));
+    CK(cudaMemsetAsync(h->f[1], 0, 19 * (size_t)h->geo.nfa * sizeof(double), h->st));
+  }
   return LBG_OK;
 }
 
@@ -631,6 +642,22 @@ int refresh_moments(lbg_handle h, double* pops_out) {
   if (h->precollision) return LBG_OK;  // mom / f[src] hold the state the driver set
   if (h->mom_valid_step == h->t && !pops_out) return LBG_OK;
   const Force& fj = force_of_last_step(h);
+  if (h->in_place) {
+    LBArgs a{};
+    a.geo = h->geo;
+    a.k = h->k;
+    a.fin = h->f[0];
+    a.fout = h->f[0];
+    a.fid_begin = own_begin(h);
+    a.fid_end = own_end(h);
+    for (int d = 0; d < 3; ++d) a.fj[d] = fj.mode == FORCE_NONE ? 0.0 : fj.u[d];
+    a.fj_field = fj.field;
+    a.ctrl = h->ctrl;
+    CK(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
+    h->launches += launch_aa_moments(a, fj.mode, h->aa_swapped, false, false, h->mom, pops_out, h->grid_aa, h->st);
+    h->mom_valid_step = h->t;
+    return LBG_OK;
+  }
   MomArgs a{};
   a.geo = h->geo;
   a.fin = h->f[h->src];
@@ -801,6 +828,7 @@ int lbg_comm_init(lbg_handle h, int nranks, int rank, const void* id) {
   if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return LBG_ERR_INVALID_ARG;
   if (nranks == 1) return LBG_OK;
   if (h->geo.zwrap) return fail(h, LBG_ERR_STATE, "lbg_comm_init needs a handle made by lbg_create_slab");
+  if (h->in_place) return fail(h, LBG_ERR_UNSUPPORTED, "in-place (AA) mode is single-slab only");
   if (!g_nccl.load()) return fail(h, LBG_ERR_NCCL, "cannot load libnccl.so.2");
   CK(cudaSetDevice(h->device));
   ncclUniqueId uid;
@@ -855,8 +883,18 @@ static void reset_lb_state(lbg_handle h) {
 
 static int zero_lb_fields(lbg_handle h) {
   const size_t nb = (size_t)h->geo.nfa * sizeof(double);
+  if (h->in_place) {  // memory-lean mode: one lattice
+    if (h->f[1]) {
+      CK(cudaStreamSynchronize(h->st));
+      cudaFree(h->f[1]);
+      h->f[1] = nullptr;
+    }
+  } else {
+    RET(ensure_second_lattice(h));
+    CK(cudaMemsetAsync(h->f[1], 0, 19 * nb, h->st));
+  }
+  h->aa_swapped = false;
   CK(cudaMemsetAsync(h->f[0], 0, 19 * nb, h->st));
-  CK(cudaMemsetAsync(h->f[1], 0, 19 * nb, h->st));
   CK(cudaMemsetAsync(h->mom, 0, 4 * nb, h->st));
   CK(cudaMemsetAsync(h->jpp[0], 0, 3 * nb, h->st));
   CK(cudaMemsetAsync(h->jpp[1], 0, 3 * nb, h->st));
@@ -917,6 +955,134 @@ int lbg_lb_time(lbg_handle h, int64_t* t) {
   return LBG_OK;
 }
 
+// In-place (AA) stepping, see lb_aa_kernels.cu.  One kernel per step, plus a moments pass on the steps
+// whose l2err is asked for (and after the last step of a call, for the negative-population guard).
+static int lb_step_in_place(lbg_handle h, double tau, int nsteps, int check_every, double target_error,
+                            double* l2err_hist, int* steps_done, int* converged) {
+  auto checked = [&](long long s) { return check_every > 0 && (s % check_every) == 0; };
+  int total = 0;
+  while (total < nsteps) {
+    const int chunk = (nsteps - total) < SLOT_CAP ? (nsteps - total) : SLOT_CAP;
+    CK(cudaMemsetAsync(h->l2_slots, 0, 2 * (size_t)chunk * sizeof(unsigned long long), h->st));
+    CK(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
+    double *scr_j = nullptr, *scr_c = nullptr;
+    Force& f_last = h->prev_equals_cur ? h->fcur : h->fprev;
+    ForceSel fs_first, fs_rest;
+    RET(select_force(h, f_last, h->fcur, &fs_first, &scr_j, &scr_c));   // first kernel: j(t) with the force of step t
+    RET(select_force(h, h->fcur, h->fcur, &fs_rest, &scr_c, &scr_c));
+    auto base_args = [&](const ForceSel& fs) {
+      LBArgs a{};
+      a.geo = h->geo;
+      a.k = h->k;
+      a.fin = h->f[0];
+      a.fout = h->f[0];
+      a.fid_begin = own_begin(h);
+      a.fid_end = own_end(h);
+      a.w1 = 1.0 - 1.0 / tau;
+      a.w2 = 1.0 / tau;
+      a.w3 = 1.0 - 1.0 / (2.0 * tau);
+      for (int d = 0; d < 3; ++d) {
+        a.fj[d] = fs.fj[d];
+        a.fc[d] = fs.fc[d];
+      }
+      a.fj_field = fs.fj_field;
+      a.fc_field = fs.fc_field;
+      a.l2_slots = h->l2_slots;
+      a.target = target_error;
+      a.ctrl = h->ctrl;
+      return a;
+    };
+    // j(t) for the first check of this call
+    if (checked(h->t + 1) && h->j_valid_step != h->t) {
+      if (h->precollision) {
+        CK(cudaMemcpyAsync(h->jpp[h->jc], h->mom + h->geo.nfa, 3 * (size_t)h->geo.nfa * sizeof(double),
+                           cudaMemcpyDeviceToDevice, h->st));
+      } else {
+        ForceSel fl;
+        RET(select_force(h, f_last, f_last, &fl, &scr_j, &scr_j));
+        LBArgs a = base_args(fl);
+        a.l2_slots = nullptr;
+        a.jnew = h->jpp[h->jc];
+        h->launches += launch_aa_moments(a, fl.mode, h->aa_swapped, false, true, nullptr, nullptr, h->grid_aa, h->st);
+      }
+      h->j_valid_step = h->t;
+    }
+    bool swapped = h->aa_swapped;
+    int jold = h->jc;
+    for (int i = 0; i < chunk; ++i) {
+      const long long s = h->t + 1 + i;
+      const ForceSel& fs = (i == 0) ? fs_first : fs_rest;
+      LBArgs a = base_args(fs);
+      a.batch_idx = i;
+      a.prev_checked = (i > 0 && checked(s - 1)) ? 1 : 0;
+      a.prev_may_stop = (s - 1 > 2) ? 1 : 0;
+      const bool first = h->precollision && i == 0;
+      h->launches += launch_aa_step(a, tau == 1.0, fs.mode, swapped, first, h->mom, h->grid_aa, h->st);
+      swapped = !swapped;
+      const bool chk = checked(s), wj = chk || checked(s + 1), last = (i == chunk - 1);
+      if (chk || wj || last) {
+        LBArgs m = base_args(fs_rest);   // the state of step s carries the force of step s in j
+        m.batch_idx = i;
+        m.jold = h->jpp[jold];
+        m.jnew = h->jpp[1 - jold];
+        h->launches += launch_aa_moments(m, fs_rest.mode, swapped, chk, wj, nullptr, nullptr, h->grid_aa, h->st);
+      }
+      jold = 1 - jold;
+    }
+    CK(cudaMemcpyAsync(h->h_l2, h->l2_slots, 2 * (size_t)chunk * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaGetLastError());
+    cudaFree(scr_j);
+    if (scr_c != scr_j) cudaFree(scr_c);
+    int executed = chunk, conv = 0, neg = 0;
+    for (int i = 0; i < chunk; ++i)
+      if (h->h_l2[2 * i + 1]) {
+        executed = i + 1;
+        neg = 1;
+        break;
+      }
+    for (int i = 0; i < executed; ++i) {
+      const long long s = h->t + 1 + i;
+      double v = std::numeric_limits<double>::quiet_NaN();
+      if (checked(s)) std::memcpy(&v, &h->h_l2[2 * i], sizeof(double));
+      if (l2err_hist) l2err_hist[total + i] = v;
+      if (neg && i == executed - 1) break;
+      if (checked(s) && s > 2 && v <= target_error) {
+        executed = i + 1;
+        conv = 1;
+        break;
+      }
+    }
+    h->t += executed;
+    if (executed > 0) {
+      h->precollision = false;
+      if (executed & 1) {
+        h->aa_swapped = !h->aa_swapped;
+        h->jc = 1 - h->jc;
+      }
+      const long long last = h->t;
+      if (checked(last) || checked(last + 1)) h->j_valid_step = last;
+      h->prev_equals_cur = true;
+    }
+    total += executed;
+    if (steps_done) *steps_done = total;
+    if (neg) return fail(h, LBG_ERR_NEGATIVE_POPULATION, lbg_status_string(LBG_ERR_NEGATIVE_POPULATION));
+    if (conv) {
+      if (converged) *converged = 1;
+      break;
+    }
+  }
+  return LBG_OK;
+}
+
+int lbg_lb_set_in_place(lbg_handle h, int on) {
+  if (!h) return LBG_ERR_INVALID_ARG;
+  if (on && h->nranks > 1) return fail(h, LBG_ERR_UNSUPPORTED, "in-place (AA) mode is single-slab only");
+  h->in_place = on != 0;
+  h->phase = PH_CREATED;  // takes effect with the next lbg_lb_init / lbg_lb_upload
+  return LBG_OK;
+}
+
 int lbg_lb_step(lbg_handle h, double tau, int nsteps, int check_every, double target_error, double* l2err_hist,
                 int* steps_done, int* converged) {
   if (!h || nsteps < 0 || check_every < 0) return LBG_ERR_INVALID_ARG;
@@ -925,6 +1091,7 @@ int lbg_lb_step(lbg_handle h, double tau, int nsteps, int check_every, double ta
   if (h->phase != PH_LB) return fail(h, LBG_ERR_STATE, "lbg_lb_step needs lbg_lb_init/lbg_lb_upload first");
   if (!(tau > 0.0) || tau < 0.5) return fail(h, LBG_ERR_RELAXATION_TIME, lbg_status_string(LBG_ERR_RELAXATION_TIME));
   CK(cudaSetDevice(h->device));
+  if (h->in_place) return lb_step_in_place(h, tau, nsteps, check_every, target_error, l2err_hist, steps_done, converged);
   auto checked = [&](long long s) { return check_every > 0 && (s % check_every) == 0; };
   int total = 0;
   while (total < nsteps) {
@@ -1015,7 +1182,16 @@ int lbg_lb_download_populations(lbg_handle h, double* n) {
   if (h->phase != PH_LB) return fail(h, LBG_ERR_STATE, "no Lattice-Boltzmann state");
   CK(cudaSetDevice(h->device));
   const double* from;
-  if (h->precollision) {
+  double* tmp = nullptr;
+  if (h->in_place) {
+    if (!h->aa_swapped) {
+      from = h->f[0];  // layout N(t) is the reference's own state
+    } else {
+      CK(cudaMalloc(&tmp, 19 * (size_t)h->geo.nfa * sizeof(double)));
+      RET(refresh_moments(h, tmp));
+      from = tmp;
+    }
+  } else if (h->precollision) {
     from = h->f[h->src];
   } else {
     // n(t) is rebuilt by a pull from n*(t); the destination buffer is used as scratch
@@ -1024,6 +1200,7 @@ int lbg_lb_download_populations(lbg_handle h, double* n) {
     from = h->f[1 - h->src];
   }
   for (int l = 0; l < 19; ++l) RET(copy_own_to_host(h, n + (size_t)l * h->nown, from + (long long)l * h->geo.nfa));
+  cudaFree(tmp);
   return LBG_OK;
 }
 
@@ -1125,7 +1302,8 @@ int lbg_mp_init(lbg_handle h, double Db, double ka, double kd, const double f_ex
   volatile double one = 1.0, three = 3.0;
   const double kBT = one / three;
   const double lambda = 4.0 * Db / kBT;
-  // Phase B aliases the population buffers
+  // Phase B aliases the population buffers (and needs the second one even after an in-place Phase A)
+  RET(ensure_second_lattice(h));
   const size_t nb = (size_t)g.nfa * sizeof(double);
   h->q = h->f[0];
   h->s = h->f[1];

@@ -161,6 +161,12 @@ int launch_collide(const CollideArgs& a, bool tau1, int fmode, int grid, cudaStr
 int launch_lb_step(const LBArgs& a, bool tau1, int fmode, bool check, bool writej, int minb, int grid,
                    cudaStream_t st);
 int launch_moments(const MomArgs& a, int fmode, int grid, cudaStream_t st);
+// in-place (AA) variant, lb_aa_kernels.cu
+int launch_aa_step(const LBArgs& a, bool tau1, int fmode, bool swapped, bool first, const double* mom, int grid,
+                   cudaStream_t st);
+int launch_aa_moments(const LBArgs& a, int fmode, bool swapped, bool check, bool writej, double* mom, double* pops,
+                      int grid, cudaStream_t st);
+int occupancy_grid_aa(int sm_count);
 int launch_fill_force(const Geo& g, long long nf, const double f[3], double* field, cudaStream_t st);
 int launch_profile(const ProfileArgs& a, int rows, cudaStream_t st);
 int launch_mp_init(const MPInitArgs& a, int grid, cudaStream_t st);

@@ -442,3 +442,102 @@ def test_full_size_config2_properties():
 def itf_not(nat):
     itf = O.detect_interfacial(nat)
     return ~((itf == 1) & (nat == 0))
+
+
+# --------------------------------------------------------------------------- in-place (AA) mode
+AA_GEOMS = [g for g in GEOMS if g[0] in ("rand6x5x7", "line1x1x22", "rand2x3x2", "rand33x7x5", "plane1x12x9", "slit8x8x16",
+                                         "onefluid3x3x3", "solidplane6x5x8", "rand40x9x6")]
+
+
+@pytest.mark.parametrize("tau", [1.0, 0.8])
+@pytest.mark.parametrize("name,mk", AA_GEOMS, ids=[g[0] for g in AA_GEOMS])
+def test_in_place_lb_steps_bit_exact(name, mk, tau):
+    """AA pattern (one population buffer): same l2err history, populations and moments as the oracle,
+    read back in both buffer layouts (after odd and even step counts), across a force switch."""
+    lb = _gpu()
+    nat = mk()
+    f = [1e-3, -2e-3, 5e-4]
+    st = O.LBState(nat, 1.0, tau)
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_set_in_place(True)
+        sim.lb_init(1.0)
+        assert np.array_equal(sim.lb_populations(), st.n)
+        ref = [st.step()[1] for _ in range(3)]
+        done, conv, h = sim.lb_step(3, tau=tau, check_every=1, target_error=-1.0)
+        assert done == 3 and np.array_equal(h, np.array(ref))
+        assert np.array_equal(sim.lb_populations(), st.n)          # swapped layout (odd number of steps)
+        st.set_force_uniform(f)
+        sim.lb_set_force_uniform(f)
+        ref = [st.step()[1] for _ in range(9)]
+        done, conv, h = sim.lb_step(9, tau=tau, check_every=1, target_error=-1.0)
+        assert done == 9 and sim.t == 12 and np.array_equal(h, np.array(ref))
+        rho, jx, jy, jz = sim.lb_moments()
+        assert np.array_equal(rho, st.rho) and np.array_equal(jx, st.jx)
+        assert np.array_equal(jy, st.jy) and np.array_equal(jz, st.jz)
+        assert np.array_equal(sim.lb_populations(), st.n)          # normal layout (even number of steps)
+        # unchecked steps, then a checked one
+        for _ in range(4):
+            st.step()
+        sim.lb_step(4, tau=tau, check_every=0)
+        e = st.step()[1]
+        done, conv, h = sim.lb_step(1, tau=tau, check_every=1, target_error=-1.0)
+        assert h[0] == e and np.array_equal(sim.lb_populations(), st.n)
+
+
+def test_in_place_equilibration_and_tracers():
+    """The whole driver flow in AA mode: exit steps, final moments, then Phase B from the resident state."""
+    lb = _gpu()
+    from laboetie_b200 import driver
+    nat = O.geometry(1, 3, 2, 14)
+    ref = O.equilibration(nat, [1e-5, 0, 0], tau=1.0, target_error=1e-10)
+    itf = O.detect_interfacial(nat)
+    mp = O.MPState(nat, itf, ref["rho"], ref["jx"], ref["jy"], ref["jz"], [1e-5, 0, 0], 0.01, 0.1, 0.01)
+    ref_v = np.array([mp.propagate()[1] for _ in range(12)])
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_set_in_place(True)
+        r = driver.equilibration(sim, [1e-5, 0, 0], tau=1.0, target_error=1e-10, chunk=97)
+        assert (r["t_exit"], r["t_fext"]) == (ref["t_exit"], ref["t_fext"])
+        assert np.array_equal(r["l2err"], ref["l2err"])
+        rho, jx, jy, jz = sim.lb_moments()
+        assert np.array_equal(jx, ref["jx"]) and np.array_equal(rho, ref["rho"])
+        assert np.array_equal(sim.lb_populations(), ref["n"])
+        d = driver.drop_tracers(sim, [1e-5, 0, 0], 0.01, 0.1, 0.01, max_steps=12)
+        P, A = sim.mp_download()
+        assert np.array_equal(P, mp.P[0]) and np.array_equal(A, mp.Pads[0])
+        assert (np.abs(d["vacf"][1:] - ref_v) <= RTOL * np.abs(mp.vacf0).max()).all()
+
+
+def test_in_place_force_field_upload_and_negative_guard():
+    lb = _gpu()
+    nat = random_nature(7, 6, 5, 0.3, 31)
+    rng = np.random.default_rng(5)
+    fl = nat == 0
+    fx, fy, fz = (np.where(fl, rng.normal(0, 1e-4, nat.shape), 0.0) for _ in range(3))
+    st = O.LBState(nat, 1.0, 0.7)
+    for _ in range(4):
+        st.step()
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_set_in_place(True)
+        sim.lb_upload(st.n, st.rho, st.jx, st.jy, st.jz)
+        st.fx[...], st.fy[...], st.fz[...] = fx, fy, fz
+        sim.lb_set_force_field(fx, fy, fz)
+        ref = [st.step()[1] for _ in range(5)]
+        done, conv, h = sim.lb_step(5, tau=0.7, check_every=1, target_error=-1.0)
+        assert np.array_equal(h, np.array(ref)) and np.array_equal(sim.lb_populations(), st.n)
+        st.fx[...], st.fy[...], st.fz[...] = 0, 0, 0
+        st.set_force_uniform([2e-4, 0, 0])
+        sim.lb_set_force_uniform([2e-4, 0, 0])
+        ref = [st.step()[1] for _ in range(4)]
+        done, conv, h = sim.lb_step(4, tau=0.7, check_every=1, target_error=-1.0)
+        assert np.array_equal(h, np.array(ref)) and np.array_equal(sim.lb_populations(), st.n)
+    nat = O.geometry(1, 4, 4, 8)
+    st = O.LBState(nat)
+    st.set_force_uniform([0.9, 0, 0])
+    t_neg = next(t for t in range(1, 20) if st.step()[0])
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_set_in_place(True)
+        sim.lb_init(1.0)
+        sim.lb_set_force_uniform([0.9, 0, 0])
+        with pytest.raises(lb.LbgError) as e:
+            sim.lb_step(50, check_every=1, target_error=-1.0)
+        assert e.value.status == 1 and sim.last_steps_done == t_neg
