@@ -113,7 +113,7 @@ def build_geometry(workload, rank, nranks):
     from laboetie_b200 import synthetic as S
     from laboetie_b200 import api
     builder, lx, ly, lz_per, f_ext, desc = S.WORKLOADS[workload]
-    weak = workload.startswith("cfg5")
+    weak = workload in S.WEAK
     lz = lz_per * nranks if weak else lz_per
     k0, nzl = api.partition(lz, nranks, rank)
     if nranks == 1:

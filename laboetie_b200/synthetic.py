@@ -135,4 +135,10 @@ WORKLOADS = {
               "synthetic random porous 1024x1024x(128 per GPU), spheres r=8, porosity~0.6, splitmix64 seed 12345"),
     "cfg5b": (bernoulli, 1024, 1024, 128, (1e-6, 0.0, 0.0),
               "synthetic Bernoulli(p_solid=0.25) hash noise 1024x1024x(128 per GPU), seed 12345"),
+    # strong-scaling configurations (fixed lattice, cut into z-slabs)
+    "cfg4": (cylinder, 512, 512, 1024, (0.0, 0.0, 1e-6), "geometryLabel=2 cylinder along z 512x512x1024"),
+    "cfg5s": (porous_spheres, 1024, 1024, 1024, (1e-6, 0.0, 0.0),
+              "synthetic random porous 1024^3 (strong scaling), spheres r=8, porosity~0.6, splitmix64 seed 12345"),
 }
+# workloads whose z extent grows with the number of GPUs (weak scaling); all others are strong
+WEAK = {"cfg5w", "cfg5b"}
