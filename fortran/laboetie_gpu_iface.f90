@@ -11,7 +11,7 @@ module laboetie_gpu
   use, intrinsic :: iso_c_binding
   implicit none
   private
-  public :: lbg_create, lbg_create_slab, lbg_destroy, lbg_comm_unique_id, lbg_comm_init, lbg_partition
+  public :: lbg_create, lbg_create_slab, lbg_create_geometry, lbg_get_nature, lbg_destroy, lbg_comm_unique_id, lbg_comm_init, lbg_partition
   public :: lbg_get_interfacial, lbg_get_counts
   public :: lbg_lb_set_in_place, lbg_lb_init, lbg_lb_upload, lbg_lb_set_force_uniform, lbg_lb_set_force_field, lbg_lb_step, lbg_lb_time
   public :: lbg_lb_download_moments, lbg_lb_download_populations, lbg_lb_profiles, lbg_lb_total_flux, lbg_lb_probe
@@ -35,6 +35,16 @@ module laboetie_gpu
       type(c_ptr), intent(out) :: h
       integer(c_int), value :: lx, ly, lz_global, k0, nzl, device
       integer(c_int8_t), intent(in) :: nature_halo(*)
+    end function
+    integer(c_int) function lbg_create_geometry(h, label, lx, ly, lz_global, k0, nzl, device) bind(C, name="lbg_create_geometry")
+      import :: c_ptr, c_int
+      type(c_ptr), intent(out) :: h
+      integer(c_int), value :: label, lx, ly, lz_global, k0, nzl, device
+    end function
+    integer(c_int) function lbg_get_nature(h, nature) bind(C, name="lbg_get_nature")
+      import :: c_ptr, c_int, c_int8_t
+      type(c_ptr), value :: h
+      integer(c_int8_t), intent(out) :: nature(*)
     end function
     integer(c_int) function lbg_destroy(h) bind(C, name="lbg_destroy")
       import :: c_ptr, c_int

@@ -80,6 +80,13 @@ int lbg_create(lbg_handle* h, int lx, int ly, int lz, const int8_t* nature, int 
  * planes k0-1 .. k0+nzl (periodic, module_system.f90:99-112). */
 int lbg_create_slab(lbg_handle* h, int lx, int ly, int lz_global, int k0, int nzl,
                     const int8_t* nature_halo, int device);
+/* the reference's exactly-representable geometry builders on the device
+ * (supercell_definition.f90:50-59): geometryLabel -1 (bulk), 1 (slit, module_geometry.f90:158-166),
+ * 2 (cylinder along z, :253-277), 3 (BCC spheres, :206-245).  Builds planes [k0, k0+nzl) of the
+ * (lx, ly, lz_global) lattice plus their periodic halo planes without any host array; k0 = 0 and
+ * nzl = lz_global gives the whole lattice on one GPU.  lbg_get_nature reads node%nature back. */
+int lbg_create_geometry(lbg_handle* h, int label, int lx, int ly, int lz_global, int k0, int nzl, int device);
+int lbg_get_nature(lbg_handle h, int8_t* nature);
 int lbg_destroy(lbg_handle h);
 /* NCCL communicator for the slab ring.  Rank 0 obtains the id, the host
  * distributes it (torch.distributed / MPI / a file), every rank calls comm_init. */

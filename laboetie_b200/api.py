@@ -24,7 +24,7 @@ STATUS = {
 # every symbol include/laboetie_gpu.h declares
 SYMBOLS = [
     "lbg_abi_version", "lbg_status_string", "lbg_last_error", "lbg_device_count", "lbg_partition", "lbg_halo_plan",
-    "lbg_create", "lbg_create_slab", "lbg_destroy", "lbg_comm_unique_id", "lbg_comm_init", "lbg_get_interfacial",
+    "lbg_create", "lbg_create_slab", "lbg_create_geometry", "lbg_get_nature", "lbg_destroy", "lbg_comm_unique_id", "lbg_comm_init", "lbg_get_interfacial",
     "lbg_get_counts", "lbg_lb_set_in_place", "lbg_lb_init", "lbg_lb_upload", "lbg_lb_set_force_uniform", "lbg_lb_set_force_field",
     "lbg_lb_step", "lbg_lb_time", "lbg_lb_download_moments", "lbg_lb_download_populations", "lbg_lb_profiles",
     "lbg_lb_total_flux", "lbg_lb_probe", "lbg_mp_init", "lbg_mp_step", "lbg_mp_download", "lbg_timer_start",
@@ -65,6 +65,8 @@ def load_library():
     L.lbg_halo_plan.argtypes = [C.POINTER(I * 5), C.POINTER(I * 5)]
     L.lbg_create.argtypes = [C.POINTER(P), I, I, I, i8, I]
     L.lbg_create_slab.argtypes = [C.POINTER(P), I, I, I, I, I, i8, I]
+    L.lbg_create_geometry.argtypes = [C.POINTER(P), I, I, I, I, I, I, I]
+    L.lbg_get_nature.argtypes = [P, i8]
     L.lbg_destroy.argtypes = [P]
     L.lbg_comm_unique_id.argtypes = [C.c_char_p]
     L.lbg_comm_init.argtypes = [P, I, I, C.c_char_p]
@@ -120,9 +122,22 @@ def comm_unique_id():
 class LaboetieGPU:
     """One GPU, one z-slab [k0, k0+nzl) of an (lx, ly, lz) lattice (the whole lattice by default)."""
 
-    def __init__(self, nature, device=0, lz_global=None, k0=0, slab=False):
+    def __init__(self, nature=None, device=0, lz_global=None, k0=0, slab=False, label=None, shape=None, nzl=None):
+        """nature: int8 (lz, ly, lx) -- or label + shape=(lx, ly, lz) to build geometryLabel -1/1/2/3 on the
+        device (lbg_create_geometry), optionally only planes [k0, k0+nzl)."""
         self._L = load_library()
         self._h = C.c_void_p()
+        if nature is None:
+            lx, ly, lz = shape
+            nzl = lz if nzl is None else nzl
+            rc = self._L.lbg_create_geometry(C.byref(self._h), int(label), lx, ly, lz, k0, nzl, device)
+            self.nzl, self.lz = nzl, lz
+            if rc:
+                self._h = C.c_void_p()
+                raise LbgError(rc, self._L.lbg_last_error(None).decode())
+            self.lx, self.ly, self.k0 = lx, ly, k0
+            self.shape = (self.nzl, ly, lx)
+            return
         nature = np.ascontiguousarray(nature, np.int8)
         if not slab:
             lz, ly, lx = nature.shape
@@ -184,6 +199,11 @@ class LaboetieGPU:
     def interfacial(self):
         out = np.zeros(self.shape, np.int8)
         self._ck(self._L.lbg_get_interfacial(self._h, out))
+        return out
+
+    def nature(self):
+        out = np.zeros(self.shape, np.int8)
+        self._ck(self._L.lbg_get_nature(self._h, out))
         return out
 
     def counts(self):

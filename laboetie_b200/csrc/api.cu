@@ -286,10 +286,11 @@ __global__ void plane_starts_kernel(Geo geo, long long ndense, long long total, 
   out[p] = (long long)w.y + __popc(w.x & ((1u << bit) - 1u));
 }
 
+// nature_halo == NULL: the geometry is built on the device from `label` (lbg_create_geometry)
 int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nzl, const int8_t* nature_halo,
-                  int device, bool zwrap) {
+                  int device, bool zwrap, int label = 0) {
   lbg_handle h = nullptr;
-  if (!out || !nature_halo || lx < 1 || ly < 1 || lz_global < 1 || nzl < 1 || k0 < 0 || k0 + nzl > lz_global)
+  if (!out || lx < 1 || ly < 1 || lz_global < 1 || nzl < 1 || k0 < 0 || k0 + nzl > lz_global)
     return fail(nullptr, LBG_ERR_INVALID_ARG, "lbg_create: invalid argument");
   const long long plane = (long long)lx * ly;
   const long long ndense = plane * (nzl + 2);
@@ -353,7 +354,8 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   h->geo.words = h->words;
   int8_t* nat_d = nullptr;
   CKB(cudaMalloc(&nat_d, (size_t)ndense));
-  CKB(cudaMemcpyAsync(nat_d, nature_halo, (size_t)ndense, cudaMemcpyHostToDevice, h->st));
+  if (nature_halo) CKB(cudaMemcpyAsync(nat_d, nature_halo, (size_t)ndense, cudaMemcpyHostToDevice, h->st));
+  else h->launches += launch_build_nature(label, lx, ly, lz_global, k0, nzl, nat_d, h->st);
   h->launches += launch_build_bits((int)plane, nzl, nat_d, h->words, h->nwords, h->st);
   h->launches += launch_scan_ranks(h->words, h->nwords, h->counts, h->st);
   unsigned long long total = 0;
@@ -772,7 +774,33 @@ int lbg_create(lbg_handle* out, int lx, int ly, int lz, const int8_t* nature, in
 
 int lbg_create_slab(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nzl, const int8_t* nature_halo,
                     int device) {
+  if (!nature_halo) return fail(nullptr, LBG_ERR_INVALID_ARG, "lbg_create_slab: nature is NULL");
   return create_common(out, lx, ly, lz_global, k0, nzl, nature_halo, device, false);
+}
+
+int lbg_create_geometry(lbg_handle* out, int label, int lx, int ly, int lz_global, int k0, int nzl, int device) {
+  if (label != -1 && label != 1 && label != 2 && label != 3)
+    return fail(nullptr, LBG_ERR_UNSUPPORTED, "lbg_create_geometry builds geometryLabel -1, 1, 2 and 3 only");
+  if (label == 2 && (lx != ly || lx < 3)) return fail(nullptr, LBG_ERR_INVALID_ARG, "wall=2 is for cylinders, which should have same lx and ly (>= 3)");
+  if (label == 3 && (lx != ly || lx != lz_global)) return fail(nullptr, LBG_ERR_INVALID_ARG, "with wall = 3, i.e. cfc cell, the supercell should be cubic with lx=ly=lz");
+  if (label == 1 && lz_global < 3 && lx * ly > 0) {
+    // two walls and nothing between them: supercell_definition.f90:84-86
+    return fail(nullptr, LBG_ERR_ALL_SOLID, lbg_status_string(LBG_ERR_ALL_SOLID));
+  }
+  const bool whole = (k0 == 0 && nzl == lz_global);
+  return create_common(out, lx, ly, lz_global, k0, nzl, nullptr, device, whole, label);
+}
+
+int lbg_get_nature(lbg_handle h, int8_t* out) {
+  if (!h || !out) return LBG_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  int8_t* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)h->nown));
+  h->launches += launch_dense_nature(h->geo, d, h->st);
+  CK(cudaMemcpyAsync(out, d, (size_t)h->nown, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  cudaFree(d);
+  return LBG_OK;
 }
 
 int lbg_destroy(lbg_handle h) {
@@ -839,9 +867,14 @@ int lbg_comm_init(lbg_handle h, int nranks, int rank, const void* id) {
   // The LB step kernel is persistent (one wave of resident blocks).  NCCL's send/recv kernel needs SM
   // room to run beside the interior planes' kernel, otherwise the exchange waits for that kernel to end:
   // leave 32 block slots free (measured at N=2: 7.7 -> 6.2 ms per step; profiles/multigpu_r1.txt).
+  // The propagate kernel gets the same treatment: its halo exchange and the lagged vacf all-reduce run
+  // beside the interior kernel.
   int reserve = 32;
   if (const char* e = std::getenv("LBG_GRID_RESERVE")) reserve = std::atoi(e);
   if (reserve > 0 && reserve < h->grid_lb) h->grid_lb -= reserve;
+  int reserve_mp = reserve;
+  if (const char* e = std::getenv("LBG_GRID_RESERVE_MP")) reserve_mp = std::atoi(e);
+  if (reserve_mp > 0 && reserve_mp < h->grid_mp) h->grid_mp -= reserve_mp;
   return LBG_OK;
 }
 

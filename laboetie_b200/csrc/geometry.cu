@@ -178,6 +178,51 @@ __global__ void __launch_bounds__(BLOCK) scatter3_aos_kernel(Geo geo, const doub
   }
 }
 
+// supercell_definition.f90:50-59 on the device, for the labels whose thresholds are exact in integer
+// arithmetic: -1 bulk, 1 slit (module_geometry.f90:158-166), 2 cylinder along z (:253-277: solid iff
+// |r - (l+1)/2| >= (lx-1)/2), 3 BCC spheres (:206-245: solid iff the distance to a cube corner or to the
+// centre is <= (lx-1)*sqrt(3)/4  <=>  16 d^2 <= 3 (lx-1)^2).  Writes planes k0-1 .. k0+nzl (periodic).
+__global__ void __launch_bounds__(BLOCK) build_nature_kernel(int label, int lx, int ly, int lz, int k0, int nzl,
+                                                             int8_t* __restrict__ nat) {
+  const long long plane = (long long)lx * ly, n = plane * (nzl + 2);
+  for (long long g = (long long)blockIdx.x * BLOCK + threadIdx.x; g < n; g += (long long)gridDim.x * BLOCK) {
+    const int p = (int)(g / plane);
+    const int rem = (int)(g - (long long)p * plane);
+    const int j = rem / lx, i = rem - j * lx;
+    int k = (k0 - 1 + p) % lz;
+    if (k < 0) k += lz;
+    bool solid = false;
+    if (label == 1) {
+      solid = (k == 0) || (k == lz - 1);
+    } else if (label == 2) {
+      const long long dx = 2LL * (i + 1) - (lx + 1), dy = 2LL * (j + 1) - (ly + 1);
+      solid = dx * dx + dy * dy >= (long long)(lx - 1) * (lx - 1);
+    } else if (label == 3) {
+      const long long thr = 3LL * (lx - 1) * (lx - 1);
+      const long long X = 2LL * (i + 1), Y = 2LL * (j + 1), Z = 2LL * (k + 1);
+      const long long cx2[2] = {2, 2LL * lx}, cy2[2] = {2, 2LL * ly}, cz2[2] = {2, 2LL * lz};
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b)
+          for (int c = 0; c < 2; ++c) {
+            const long long d2 = (X - cx2[a]) * (X - cx2[a]) + (Y - cy2[b]) * (Y - cy2[b]) + (Z - cz2[c]) * (Z - cz2[c]);
+            solid = solid || (4 * d2 <= thr);
+          }
+      const long long mx = lx + 1, my = ly + 1, mz = lz + 1;
+      solid = solid || (4 * ((X - mx) * (X - mx) + (Y - my) * (Y - my) + (Z - mz) * (Z - mz)) <= thr);
+    }
+    nat[g] = solid ? 1 : 0;
+  }
+}
+
+// node%nature of the own planes back from the rank structure
+__global__ void __launch_bounds__(BLOCK) dense_nature_kernel(Geo geo, int8_t* __restrict__ out) {
+  const long long nown = (long long)geo.plane * geo.nzl;
+  for (long long q = (long long)blockIdx.x * BLOCK + threadIdx.x; q < nown; q += (long long)gridDim.x * BLOCK) {
+    int fid;
+    out[q] = lookup(geo, (int)(q + geo.plane), fid) ? 0 : 1;
+  }
+}
+
 inline int big_grid(long long n) {
   const long long b = (n + BLOCK - 1) / BLOCK;
   return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
@@ -188,6 +233,16 @@ inline int big_grid(long long n) {
 int launch_build_bits(int plane, int nzl, const int8_t* nature_halo, uint2* words, long long nwords, cudaStream_t st) {
   const long long ndense = (long long)plane * (nzl + 2);
   build_bits_kernel<<<big_grid(nwords * 32), BLOCK, 0, st>>>(ndense, nature_halo, words, nwords);
+  return 1;
+}
+
+int launch_build_nature(int label, int lx, int ly, int lz, int k0, int nzl, int8_t* nature_halo, cudaStream_t st) {
+  build_nature_kernel<<<big_grid((long long)lx * ly * (nzl + 2)), BLOCK, 0, st>>>(label, lx, ly, lz, k0, nzl, nature_halo);
+  return 1;
+}
+
+int launch_dense_nature(const Geo& g, int8_t* out_own, cudaStream_t st) {
+  dense_nature_kernel<<<big_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, out_own);
   return 1;
 }
 

@@ -144,6 +144,8 @@ struct ProfileArgs {
 // launchers (geometry.cu / lb_kernels.cu / mp_kernels.cu).  Each returns the number of kernels launched.
 int launch_build_bits(int plane, int nzl, const int8_t* nature_halo, uint2* words, long long nwords, cudaStream_t st);
 int launch_scan_ranks(uint2* words, long long nwords, unsigned long long* total, cudaStream_t st);
+int launch_build_nature(int label, int lx, int ly, int lz, int k0, int nzl, int8_t* nature_halo, cudaStream_t st);
+int launch_dense_nature(const Geo& g, int8_t* out_own, cudaStream_t st);
 int launch_build_gidx(const Geo& g, long long nwords, uint32_t* gidx, cudaStream_t st);
 int launch_rank_at(const Geo& g, const long long* dense_idx, int n, long long ndense, long long total, long long* out,
                    cudaStream_t st);

@@ -541,3 +541,30 @@ def test_in_place_force_field_upload_and_negative_guard():
         with pytest.raises(lb.LbgError) as e:
             sim.lb_step(50, check_every=1, target_error=-1.0)
         assert e.value.status == 1 and sim.last_steps_done == t_neg
+
+
+@pytest.mark.parametrize("label,shape", [(-1, (5, 4, 3)), (1, (4, 3, 9)), (2, (11, 11, 4)), (2, (26, 26, 3)), (3, (9, 9, 9)),
+                                          (3, (16, 16, 16)), (3, (33, 33, 33))])
+def test_device_side_geometry_builders(label, shape):
+    """geometryLabel -1/1/2/3 built on the device equal the reference's builders (oracle),
+    whole lattice and as a z-slab; flow on the device-built lattice equals flow on the host-built one."""
+    lb = _gpu()
+    nat = O.geometry(label, *shape)
+    with lb.LaboetieGPU(label=label, shape=shape) as sim:
+        assert np.array_equal(sim.nature(), nat)
+        assert np.array_equal(sim.interfacial(), O.detect_interfacial(nat))
+        sim.lb_init(1.0)
+        sim.lb_set_force_uniform([1e-4, 0, 2e-4])
+        sim.lb_step(5, check_every=0)
+        n_dev = sim.lb_populations()
+    st = O.LBState(nat)
+    st.set_force_uniform([1e-4, 0, 2e-4])
+    for _ in range(5):
+        st.step()
+    assert np.array_equal(n_dev, st.n)
+    lz = shape[2]
+    if lz >= 4:
+        k0, nzl = 1, lz - 2
+        with lb.LaboetieGPU(label=label, shape=shape, k0=k0, nzl=nzl) as slab:
+            assert np.array_equal(slab.nature(), nat[k0:k0 + nzl])
+            assert np.array_equal(slab.interfacial(), O.detect_interfacial(nat)[k0:k0 + nzl])
