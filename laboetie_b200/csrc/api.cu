@@ -17,6 +17,7 @@
 // ncclAllReduce.  NCCL is loaded with dlopen only when lbg_comm_init is called.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
 
 #include <climits>
 #include <cmath>
@@ -110,10 +111,21 @@ struct lbg_handle_s {
 
   int nranks = 1, rank = 0;
   ncclComm_t comm = nullptr;
-  cudaStream_t st = nullptr, st_comm = nullptr;
+  cudaStream_t st = nullptr, st_comm = nullptr, st_ar = nullptr;  // compute, halo traffic, scalar all-reduces
   cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   cudaEvent_t ev_ar[2] = {nullptr, nullptr};  // lagged vacf all-reduces of Phase B
+  cudaEvent_t ev_arb = nullptr;               // blocking all-reduce on the all-reduce stream
   bool halo_pending = false;
+  // peer-to-peer halos (NVLink, copy engines): neighbours' population buffers and arrival flags
+  bool p2p = false;
+  double* peer_f[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [down/up][buffer]
+  unsigned int* peer_flags[2] = {nullptr, nullptr};                 // [down/up]
+  bool peer_ipc[2] = {false, false};                                // opened with cudaIpcOpenMemHandle
+  long long peer_nfa[2] = {0, 0}, peer_hi_halo[2] = {0, 0};         // neighbour's stride / first fid of its upper halo
+  unsigned int* flags = nullptr;   // [0] = halo data from the lower neighbour has arrived up to this sequence number, [1] = upper
+  unsigned int xseq = 0;           // exchanges issued so far
+  unsigned int xwait = 0;          // sequence number the next kernels must see in flags[]
+  int* p2p_err = nullptr;          // set by a wait kernel that timed out
 
   uint2* words = nullptr;
   uint32_t* gidx = nullptr;
@@ -222,11 +234,69 @@ long long own_end(const lbg_handle h) { return h->pstart[h->geo.nzl + 1]; }
 int up_rank(const lbg_handle h) { return (h->rank + 1) % h->nranks; }
 int down_rank(const lbg_handle h) { return (h->rank + h->nranks - 1) % h->nranks; }
 
+// peer flag store after the pushes of one exchange (copy engine traffic precedes it in stream order)
+__global__ void p2p_signal_kernel(unsigned int* flag_a, unsigned int* flag_b, unsigned int seq) {
+  __threadfence_system();
+  if (flag_a) *(volatile unsigned int*)flag_a = seq;
+  if (flag_b) *(volatile unsigned int*)flag_b = seq;
+  __threadfence_system();
+}
+
+// wait until both neighbours' halo data of exchange `seq` have landed; bounded spin (no GPU hang if a
+// neighbour died): on time-out the control block's stop flag is raised and *err set
+__global__ void p2p_wait_kernel(const unsigned int* flags, unsigned int seq, Ctrl* ctrl, int* err) {
+  const long long t0 = clock64();
+  for (;;) {
+    const unsigned int a = *(volatile const unsigned int*)&flags[0];
+    const unsigned int b = *(volatile const unsigned int*)&flags[1];
+    if ((int)(a - seq) >= 0 && (int)(b - seq) >= 0) break;
+    if (clock64() - t0 > 40000000000LL) {  // ~20 s
+      ctrl->stop = 1;
+      *err = 2;
+      break;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
+int halo_exchange_p2p(lbg_handle h, double* base, const int* up_list, int nup, const int* down_list, int ndown) {
+  const Geo& g = h->geo;
+  const std::vector<long long>& ps = h->pstart;
+  const int nz = g.nzl;
+  const int b = (base >= h->f[1] && base < h->f[1] + 19 * g.nfa) ? 1 : 0;
+  const long long base_off = base - h->f[b];                   // offset of the field inside its buffer, in my stride
+  const long long first_arr = base_off / g.nfa;                // fields start on array boundaries
+  const size_t top_cnt = (size_t)(ps[nz + 1] - ps[nz]), bot_cnt = (size_t)(ps[2] - ps[1]);
+  CK(cudaEventRecord(h->ev_ready, h->st));
+  CK(cudaStreamWaitEvent(h->st_comm, h->ev_ready, 0));
+  for (int i = 0; i < nup && top_cnt; ++i) {   // my top plane -> lower halo of the upper neighbour (its fids 0..)
+    const double* src = base + (long long)up_list[i] * g.nfa + ps[nz];
+    double* dst = h->peer_f[1][b] + (first_arr + up_list[i]) * h->peer_nfa[1];
+    CK(cudaMemcpyAsync(dst, src, top_cnt * sizeof(double), cudaMemcpyDeviceToDevice, h->st_comm));
+  }
+  for (int i = 0; i < ndown && bot_cnt; ++i) {  // my bottom plane -> upper halo of the lower neighbour
+    const double* src = base + (long long)down_list[i] * g.nfa + ps[1];
+    double* dst = h->peer_f[0][b] + (first_arr + down_list[i]) * h->peer_nfa[0] + h->peer_hi_halo[0];
+    CK(cudaMemcpyAsync(dst, src, bot_cnt * sizeof(double), cudaMemcpyDeviceToDevice, h->st_comm));
+  }
+  ++h->xseq;
+  // upper neighbour: I am its lower side -> flags[0]; lower neighbour: I am its upper side -> flags[1]
+  p2p_signal_kernel<<<1, 1, 0, h->st_comm>>>(h->peer_flags[1] + 0, h->peer_flags[0] + 1, h->xseq);
+  h->launches += 1;
+  CK(cudaEventRecord(h->ev_halo, h->st_comm));
+  h->halo_pending = true;
+  h->xwait = h->xseq;
+  return LBG_OK;
+}
+
 // Exchange boundary planes with the ring neighbours.  up_list / down_list name the arrays (index into
 // base, stride nfa) whose top own plane goes to the upper neighbour's lower halo / whose bottom own
 // plane goes to the lower neighbour's upper halo.  Runs on st_comm after everything enqueued on st.
 int halo_exchange(lbg_handle h, double* base, const int* up_list, int nup, const int* down_list, int ndown) {
   if (h->nranks == 1) return LBG_OK;
+  if (h->p2p && ((base >= h->f[0] && base < h->f[0] + 19 * h->geo.nfa) || (h->f[1] && base >= h->f[1] && base < h->f[1] + 19 * h->geo.nfa)))
+    return halo_exchange_p2p(h, base, up_list, nup, down_list, ndown);
   const Geo& g = h->geo;
   const std::vector<long long>& ps = h->pstart;
   const int nz = g.nzl;
@@ -256,6 +326,20 @@ int wait_halo(lbg_handle h) {
     CK(cudaStreamWaitEvent(h->st, h->ev_halo, 0));
     h->halo_pending = false;
   }
+  if (h->p2p && h->xwait) {  // the neighbours' pushes of the latest exchange must have landed
+    p2p_wait_kernel<<<1, 1, 0, h->st>>>(h->flags, h->xwait, h->ctrl, h->p2p_err);
+    h->launches += 1;
+    h->xwait = 0;
+  }
+  return LBG_OK;
+}
+
+// after a batch has been synchronised: did a halo wait give up?
+int check_p2p(lbg_handle h) {
+  if (!h->p2p) return LBG_OK;
+  int e = 0;
+  CK(cudaMemcpy(&e, h->p2p_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) return fail(h, LBG_ERR_NCCL, "timed out waiting for a neighbour's halo planes (peer-to-peer exchange)");
   return LBG_OK;
 }
 
@@ -263,13 +347,23 @@ const int UP_L[5] = {5, 11, 12, 15, 16};     // cz = +1  (reference l = 6,12,13,
 const int DOWN_L[5] = {6, 13, 14, 17, 18};   // cz = -1  (reference l = 7,14,15,18,19)
 
 // all-reduce in place across the ring, ordered after st, result visible to st after wait_halo
+// With peer-to-peer halos NCCL is only used for these scalars, on its own stream, so that the copy-engine
+// pushes of the next exchange never queue behind an all-reduce that waits for every rank.
+cudaStream_t ar_stream(const lbg_handle h) { return h->p2p ? h->st_ar : h->st_comm; }
+
 int allreduce(lbg_handle h, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t op) {
   if (h->nranks == 1) return LBG_OK;
+  cudaStream_t sa = ar_stream(h);
   CK(cudaEventRecord(h->ev_ready, h->st));
-  CK(cudaStreamWaitEvent(h->st_comm, h->ev_ready, 0));
-  NK(g_nccl.AllReduce(buf, buf, n, dt, op, h->comm, h->st_comm));
-  CK(cudaEventRecord(h->ev_halo, h->st_comm));
-  h->halo_pending = true;
+  CK(cudaStreamWaitEvent(sa, h->ev_ready, 0));
+  NK(g_nccl.AllReduce(buf, buf, n, dt, op, h->comm, sa));
+  if (h->p2p) {  // blocking use: the compute stream continues once the result is there
+    CK(cudaEventRecord(h->ev_arb, sa));
+    CK(cudaStreamWaitEvent(h->st, h->ev_arb, 0));
+  } else {
+    CK(cudaEventRecord(h->ev_halo, sa));
+    h->halo_pending = true;
+  }
   return LBG_OK;
 }
 
@@ -330,8 +424,10 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   h->sm_count = prop.multiProcessorCount;
   CKB(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
   CKB(cudaStreamCreateWithFlags(&h->st_comm, cudaStreamNonBlocking));
+  CKB(cudaStreamCreateWithFlags(&h->st_ar, cudaStreamNonBlocking));
   CKB(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
   CKB(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+  CKB(cudaEventCreateWithFlags(&h->ev_arb, cudaEventDisableTiming));
   CKB(cudaEventCreateWithFlags(&h->ev_ar[0], cudaEventDisableTiming));
   CKB(cudaEventCreateWithFlags(&h->ev_ar[1], cudaEventDisableTiming));
   CKB(cudaEventCreate(&h->ev_t0));
@@ -808,6 +904,15 @@ int lbg_destroy(lbg_handle h) {
   cudaSetDevice(h->device);
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->st_comm) cudaStreamSynchronize(h->st_comm);
+  if (h->st_ar) cudaStreamSynchronize(h->st_ar);
+  for (int s = 0; s < 2; ++s)
+    if (h->peer_ipc[s]) {
+      cudaIpcCloseMemHandle(h->peer_f[s][0]);
+      cudaIpcCloseMemHandle(h->peer_f[s][1]);
+      cudaIpcCloseMemHandle(h->peer_flags[s]);
+    }
+  cudaFree(h->flags);
+  cudaFree(h->p2p_err);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->words);
   cudaFree(h->gidx);
@@ -831,12 +936,14 @@ int lbg_destroy(lbg_handle h) {
   cudaFreeHost(h->h_ctrl);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   if (h->ev_halo) cudaEventDestroy(h->ev_halo);
+  if (h->ev_arb) cudaEventDestroy(h->ev_arb);
   if (h->ev_ar[0]) cudaEventDestroy(h->ev_ar[0]);
   if (h->ev_ar[1]) cudaEventDestroy(h->ev_ar[1]);
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
   if (h->st) cudaStreamDestroy(h->st);
   if (h->st_comm) cudaStreamDestroy(h->st_comm);
+  if (h->st_ar) cudaStreamDestroy(h->st_ar);
   delete h;
   return LBG_OK;
 }
@@ -864,15 +971,104 @@ int lbg_comm_init(lbg_handle h, int nranks, int rank, const void* id) {
   NK(g_nccl.CommInitRank(&h->comm, nranks, uid, rank));
   h->nranks = nranks;
   h->rank = rank;
+  // ---- peer-to-peer halos: map the ring neighbours' population buffers and flags (same node, NVLink)
+  {
+    struct PeerInfo {
+      int pid, dev;
+      cudaIpcMemHandle_t f0, f1, fl;
+      unsigned long long f0_ptr, f1_ptr, fl_ptr;
+      long long nfa, hi_halo;
+      int ok;
+    };
+    int want = 1;
+    if (const char* e = std::getenv("LBG_HALO")) want = std::strcmp(e, "nccl") != 0;
+    RET(ensure_second_lattice(h));
+    CK(cudaMalloc(&h->flags, 8 * sizeof(unsigned int)));
+    CK(cudaMemsetAsync(h->flags, 0, 8 * sizeof(unsigned int), h->st));
+    CK(cudaMalloc(&h->p2p_err, sizeof(int)));
+    CK(cudaMemsetAsync(h->p2p_err, 0, sizeof(int), h->st));
+    PeerInfo me{};
+    me.pid = (int)getpid();
+    me.dev = h->device;
+    me.ok = want;
+    if (cudaIpcGetMemHandle(&me.f0, h->f[0]) != cudaSuccess) me.ok = 0;
+    if (cudaIpcGetMemHandle(&me.f1, h->f[1]) != cudaSuccess) me.ok = 0;
+    if (cudaIpcGetMemHandle(&me.fl, h->flags) != cudaSuccess) me.ok = 0;
+    cudaGetLastError();
+    me.f0_ptr = (unsigned long long)h->f[0];
+    me.f1_ptr = (unsigned long long)h->f[1];
+    me.fl_ptr = (unsigned long long)h->flags;
+    me.nfa = h->geo.nfa;
+    me.hi_halo = h->pstart[h->geo.nzl + 1];
+    std::vector<PeerInfo> all((size_t)nranks);
+    PeerInfo *d_me = nullptr, *d_all = nullptr;
+    CK(cudaMalloc(&d_me, sizeof(PeerInfo)));
+    CK(cudaMalloc(&d_all, sizeof(PeerInfo) * (size_t)nranks));
+    CK(cudaMemcpyAsync(d_me, &me, sizeof(PeerInfo), cudaMemcpyHostToDevice, h->st));
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    *(void**)(&AllGather) = dlsym(g_nccl.lib, "ncclAllGather");
+    if (!AllGather) return fail(h, LBG_ERR_NCCL, "ncclAllGather not found");
+    NK(AllGather(d_me, d_all, sizeof(PeerInfo), ncclChar, h->comm, h->st));
+    CK(cudaMemcpyAsync(all.data(), d_all, sizeof(PeerInfo) * (size_t)nranks, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    cudaFree(d_me);
+    cudaFree(d_all);
+    bool ok = true;
+    for (const PeerInfo& p : all) ok = ok && p.ok;
+    const int nbr[2] = {down_rank(h), up_rank(h)};
+    for (int s = 0; s < 2 && ok; ++s) {
+      const PeerInfo& p = all[(size_t)nbr[s]];
+      h->peer_nfa[s] = p.nfa;
+      h->peer_hi_halo[s] = p.hi_halo;
+      if (p.pid == me.pid) {  // several slabs driven from one process: plain peer access
+        if (p.dev != h->device) {
+          cudaError_t e = cudaDeviceEnablePeerAccess(p.dev, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+          cudaGetLastError();
+        }
+        h->peer_f[s][0] = (double*)p.f0_ptr;
+        h->peer_f[s][1] = (double*)p.f1_ptr;
+        h->peer_flags[s] = (unsigned int*)p.fl_ptr;
+        h->peer_ipc[s] = false;
+      } else if (s == 1 && nbr[1] == nbr[0]) {  // two slabs: the same neighbour on both sides, map once
+        h->peer_f[1][0] = h->peer_f[0][0];
+        h->peer_f[1][1] = h->peer_f[0][1];
+        h->peer_flags[1] = h->peer_flags[0];
+        h->peer_ipc[1] = false;
+      } else {
+        void *a = nullptr, *b = nullptr, *c = nullptr;
+        if (cudaIpcOpenMemHandle(&a, p.f0, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&b, p.f1, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&c, p.fl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          ok = false;
+          cudaGetLastError();
+        }
+        h->peer_f[s][0] = (double*)a;
+        h->peer_f[s][1] = (double*)b;
+        h->peer_flags[s] = (unsigned int*)c;
+        h->peer_ipc[s] = true;
+      }
+    }
+    // every rank must take the same path: agree on the outcome
+    int* d_ok = h->mp_err;
+    int okv = ok ? 1 : 0;
+    CK(cudaMemcpyAsync(d_ok, &okv, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    NK(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, h->comm, h->st));
+    CK(cudaMemcpyAsync(&okv, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->p2p = okv != 0;
+  }
   // The LB step kernel is persistent (one wave of resident blocks).  NCCL's send/recv kernel needs SM
   // room to run beside the interior planes' kernel, otherwise the exchange waits for that kernel to end:
   // leave 32 block slots free (measured at N=2: 7.7 -> 6.2 ms per step; profiles/multigpu_r1.txt).
   // The propagate kernel gets the same treatment: its halo exchange and the lagged vacf all-reduce run
   // beside the interior kernel.
-  int reserve = 32;
+  // With peer-to-peer halos the copy engines move the planes and only the small scalar all-reduces
+  // need an SM, and they run between kernels: nothing is reserved.
+  int reserve = h->p2p ? 0 : 32;
   if (const char* e = std::getenv("LBG_GRID_RESERVE")) reserve = std::atoi(e);
   if (reserve > 0 && reserve < h->grid_lb) h->grid_lb -= reserve;
-  int reserve_mp = reserve;
+  int reserve_mp = h->p2p ? 0 : 32;
   if (const char* e = std::getenv("LBG_GRID_RESERVE_MP")) reserve_mp = std::atoi(e);
   if (reserve_mp > 0 && reserve_mp < h->grid_mp) h->grid_mp -= reserve_mp;
   return LBG_OK;
@@ -1154,6 +1350,7 @@ int lbg_lb_step(lbg_handle h, double tau, int nsteps, int check_every, double ta
     CK(cudaMemcpyAsync(h->h_ctrl, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     CK(cudaGetLastError());
+    RET(check_p2p(h));
     if (scr) cudaFree(scr);
     int executed = chunk, conv = 0, neg = 0;
     for (int i = 0; i < chunk; ++i)
@@ -1428,7 +1625,10 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
     // The stop test needs the global vacf of a step.  On one GPU step i looks at step i-1.  Across GPUs
     // the all-reduce of step i is left a whole step to complete: step i looks at step i-2, so at most
     // one step runs past the converged one -- and its input buffers are exactly the wanted state.
-    const int lag = h->nranks > 1 ? 2 : 1;
+    // Measured at N=2 (profiles/multigpu_r1.txt): with peer-to-peer halos the plain blocking all-reduce is
+    // fastest (the GPU is otherwise idle at that point); the lagged one only pays off on the NCCL path.
+    int lag = (h->nranks > 1 && !h->p2p) ? 2 : 1;
+    if (const char* e = std::getenv("LBG_MP_LAG")) lag = (h->nranks > 1 && std::atoi(e) == 2) ? 2 : 1;
     for (int i = 0; i < chunk; ++i) {
       const long long it = h->it + 1 + i;
       MPArgs a{};
@@ -1468,27 +1668,34 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
         launch(own_begin(h), own_end(h), true);
       } else {
         const int all3[3] = {0, 1, 2};
-        if (i >= 2) CK(cudaStreamWaitEvent(h->st, h->ev_ar[i & 1], 0));  // all-reduce of step i-2
+        if (lag == 2 && i >= 2) CK(cudaStreamWaitEvent(h->st, h->ev_ar[i & 1], 0));  // all-reduce of step i-2
         launch(ps[1], ps[2]);
         if (nz > 1) launch(ps[nz], ps[nz + 1]);
         RET(halo_exchange(h, h->P[1 - pc], all3, 3, all3, 3));
         if (nz > 2) launch(ps[2], ps[nz], true);
+        if (lag == 1) {  // blocking variant: the next step waits for this step's global vacf
+          RET(wait_halo(h));
+          RET(allreduce(h, h->vacf_slots + 3 * i, 3, ncclDouble, ncclSum));
+          pc = 1 - pc;
+          continue;
+        }
         // all-reduce of this step's vacf on the communication stream, not waited for here
         CK(cudaEventRecord(h->ev_ready, h->st));
-        CK(cudaStreamWaitEvent(h->st_comm, h->ev_ready, 0));
-        NK(g_nccl.AllReduce(h->vacf_slots + 3 * i, h->vacf_slots + 3 * i, 3, ncclDouble, ncclSum, h->comm, h->st_comm));
-        CK(cudaEventRecord(h->ev_ar[i & 1], h->st_comm));
+        CK(cudaStreamWaitEvent(ar_stream(h), h->ev_ready, 0));
+        NK(g_nccl.AllReduce(h->vacf_slots + 3 * i, h->vacf_slots + 3 * i, 3, ncclDouble, ncclSum, h->comm, ar_stream(h)));
+        CK(cudaEventRecord(h->ev_ar[i & 1], ar_stream(h)));
       }
       pc = 1 - pc;
     }
     RET(wait_halo(h));
-    if (h->nranks > 1) {
+    if (h->nranks > 1 && lag == 2) {
       CK(cudaStreamWaitEvent(h->st, h->ev_ar[0], 0));
       CK(cudaStreamWaitEvent(h->st, h->ev_ar[1], 0));
     }
     CK(cudaMemcpyAsync(h->h_vacf, h->vacf_slots, (size_t)chunk * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     CK(cudaGetLastError());
+    RET(check_p2p(h));
     int executed = chunk, conv = 0, ran = chunk;
     for (int i = 0; i < chunk; ++i) {
       const long long it = h->it + 1 + i;
@@ -1562,6 +1769,7 @@ int lbg_sync(lbg_handle h) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->st));
   CK(cudaStreamSynchronize(h->st_comm));
+  CK(cudaStreamSynchronize(h->st_ar));
   return LBG_OK;
 }
 
