@@ -40,6 +40,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TRACER = dict(Db=0.01, ka=0.1, kd=0.01)   # README example values (README.md:129-133)
+if os.environ.get("LBG_BENCH_KA"):    # tuning runs only (e.g. 0 switches adsorption off)
+    TRACER["ka"] = float(os.environ["LBG_BENCH_KA"])
 TAU = 1.0
 
 

@@ -367,6 +367,18 @@ int allreduce(lbg_handle h, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t 
   return LBG_OK;
 }
 
+// With one-sided pushes a neighbour may write into my halo ranges as soon as IT is ready.  After a
+// (re)initialisation that clears the buffers, nobody may start pushing before every rank is done
+// clearing: a barrier across the ring (an all-reduce that every rank reaches after its own memsets).
+int ring_barrier(lbg_handle h) {
+  if (h->nranks == 1) return LBG_OK;
+  CK(cudaMemsetAsync(h->counts, 0, sizeof(unsigned long long), h->st));
+  RET(allreduce(h, h->counts, 1, ncclUint64, ncclSum));
+  RET(wait_halo(h));
+  CK(cudaStreamSynchronize(h->st));
+  return LBG_OK;
+}
+
 __global__ void plane_starts_kernel(Geo geo, long long ndense, long long total, long long* out) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p > geo.nzl + 2) return;
@@ -1137,6 +1149,7 @@ int lbg_lb_init(lbg_handle h, double rho0) {
   h->launches += launch_lb_init(h->geo, own_begin(h), own_end(h), rho0, h->k.a0, h->f[0], h->mom, h->st);
   CK(cudaGetLastError());
   reset_lb_state(h);
+  RET(ring_barrier(h));
   return LBG_OK;
 }
 
@@ -1149,6 +1162,7 @@ int lbg_lb_upload(lbg_handle h, const double* n, const double* rho, const double
   const double* m[4] = {rho, jx, jy, jz};
   for (int c = 0; c < 4; ++c) RET(copy_own_to_device(h, h->mom + (long long)c * h->geo.nfa, m[c]));
   reset_lb_state(h);
+  RET(ring_barrier(h));
   return LBG_OK;
 }
 

@@ -70,8 +70,25 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Tiles of BLOCK consecutive fids start on a 32-fid boundary whatever fid_begin is (a plane may start at
+// any fid): every warp then reads and writes whole, aligned 256-byte runs of each array.  Threads of
+// the first tile that fall before fid_begin skip (`ff < fid_begin`).
+#ifndef LBG_ALIGN_TILES
+#define LBG_ALIGN_TILES 1
+#endif
+__host__ __device__ __forceinline__ long long tile_base(long long fid_begin) {
+#if LBG_ALIGN_TILES
+  return fid_begin & ~31LL;
+#else
+  return fid_begin;
+#endif
+}
+__device__ __forceinline__ long long first_fid(long long fid_begin) {
+  return tile_base(fid_begin) + (long long)blockIdx.x * BLOCK + threadIdx.x;
+}
+
 inline int clamp_grid(long long n, int grid) {
-  const long long b = (n + BLOCK - 1) / BLOCK;
+  const long long b = (n + 31 + BLOCK - 1) / BLOCK;  // + 31: tiles start on the 32-fid boundary below fid_begin
   return (int)(b < 1 ? 1 : (b < grid ? b : grid));
 }
 

@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(BLOCK, 2) aa_even_kernel(const __grid_constant
   if (s_stop) return;
   const long long nfa = a.geo.nfa;
   double* f = a.fout;  // in place: fin == fout
-  for (long long ff = a.fid_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; ff < a.fid_end;
-       ff += (long long)gridDim.x * BLOCK) {
+  for (long long ff = first_fid(a.fid_begin); ff < a.fid_end; ff += (long long)gridDim.x * BLOCK) {
+    if (ff < a.fid_begin) continue;
     const int fid = (int)ff;
     double n[NV];
     static_for<0, NV>([&](auto Lc) {
@@ -109,12 +109,13 @@ __global__ void __launch_bounds__(BLOCK, 2) aa_odd_kernel(const __grid_constant_
   const Geo& geo = a.geo;
   const long long nfa = geo.nfa;
   double* f = a.fout;
-  const long long first = a.fid_begin + (long long)blockIdx.x * BLOCK + threadIdx.x;
+  const long long first = first_fid(a.fid_begin);
   const long long stride = (long long)gridDim.x * BLOCK;
   uint32_t gi_next = first < a.fid_end ? __ldg(geo.gidx + first) : 0u;
   for (long long ff = first; ff < a.fid_end; ff += stride) {
     const uint32_t gi = gi_next;
     if (ff + stride < a.fid_end) gi_next = __ldg(geo.gidx + ff + stride);
+    if (ff < a.fid_begin) continue;
     const int fid = (int)ff;
     const int g = (int)(gi & GIDX_MASK);
     const Nb nb = neighbours(geo, g);
@@ -175,8 +176,8 @@ __global__ void __launch_bounds__(BLOCK, 2) aa_moments_kernel(const __grid_const
   const double* f = a.fin;
   double dmax = 0.0;
   bool any_neg = false;
-  for (long long ff = a.fid_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; ff < a.fid_end;
-       ff += (long long)gridDim.x * BLOCK) {
+  for (long long ff = first_fid(a.fid_begin); ff < a.fid_end; ff += (long long)gridDim.x * BLOCK) {
+    if (ff < a.fid_begin) continue;
     const int fid = (int)ff;
     double n[NV];
     if constexpr (!SWAPPED) {

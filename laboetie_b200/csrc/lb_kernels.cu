@@ -89,12 +89,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_const
   bool any_neg = false;
   // tiles of BLOCK consecutive fluid nodes; the dense index of the next tile's node is fetched one
   // iteration ahead so that its DRAM latency does not sit in front of the dependent population loads
-  const long long first = a.fid_begin + (long long)blockIdx.x * BLOCK + threadIdx.x;
+  const long long first = first_fid(a.fid_begin);
   const long long stride = (long long)gridDim.x * BLOCK;
   uint32_t gi_next = first < a.fid_end ? __ldg(geo.gidx + first) : 0u;
   for (long long ff = first; ff < a.fid_end; ff += stride) {
     const uint32_t gi = gi_next;
     if (ff + stride < a.fid_end) gi_next = __ldg(geo.gidx + ff + stride);
+    if (ff < a.fid_begin) continue;
     const int fid = (int)ff;
     const int g = (int)(gi & GIDX_MASK);
     const Nb nb = neighbours(geo, g);
@@ -148,8 +149,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_const
 template <bool TAU1, int FMODE>
 __global__ void __launch_bounds__(BLOCK) collide_kernel(const __grid_constant__ CollideArgs a) {
   const long long nfa = a.geo.nfa;
-  for (long long ff = a.fid_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; ff < a.fid_end;
-       ff += (long long)gridDim.x * BLOCK) {
+  for (long long ff = first_fid(a.fid_begin); ff < a.fid_end; ff += (long long)gridDim.x * BLOCK) {
+    if (ff < a.fid_begin) continue;
     const int fid = (int)ff;
     double n[NV];
     static_for<0, NV>([&](auto Lc) {
@@ -174,8 +175,8 @@ __global__ void __launch_bounds__(BLOCK) collide_kernel(const __grid_constant__ 
 template <int FMODE>
 __global__ void __launch_bounds__(BLOCK) moments_kernel(const __grid_constant__ MomArgs a) {
   const long long nfa = a.geo.nfa;
-  for (long long ff = a.fid_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; ff < a.fid_end;
-       ff += (long long)gridDim.x * BLOCK) {
+  for (long long ff = first_fid(a.fid_begin); ff < a.fid_end; ff += (long long)gridDim.x * BLOCK) {
+    if (ff < a.fid_begin) continue;
     const int fid = (int)ff;
     const int g = (int)(a.geo.gidx[fid] & GIDX_MASK);
     const Nb nb = neighbours(a.geo, g);

@@ -19,6 +19,9 @@
 // overwritten every step (solid nodes own no storage).
 #include "lattice.cuh"
 
+#ifndef LBG_MP_EXP
+#define LBG_MP_EXP 0
+#endif
 #ifndef LBG_MP_MINB
 #define LBG_MP_MINB 2
 #endif
@@ -72,8 +75,8 @@ __global__ void __launch_bounds__(BLOCK) mp_init_kernel(const __grid_constant__ 
   const double eps = 2.220446049250313e-16;  // epsilon(1._dp)
   double v0x = 0, v0y = 0, v0z = 0;
   bool bad = false;
-  for (long long ff = a.fid_begin + (long long)blockIdx.x * BLOCK + threadIdx.x; ff < a.fid_end;
-       ff += (long long)gridDim.x * BLOCK) {
+  for (long long ff = first_fid(a.fid_begin); ff < a.fid_end; ff += (long long)gridDim.x * BLOCK) {
+    if (ff < a.fid_begin) continue;
     const int fid = (int)ff;
     const uint32_t gi = geo.gidx[fid];
     const int g = (int)(gi & GIDX_MASK);
@@ -168,12 +171,13 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
   // into strips of rows and all planes of a strip are visited before the next strip, so the three
   // planes a node gathers P from were touched a few MB of traffic ago and are still in L2: P is then
   // read from HBM once per step instead of up to three times.
-  const int ntiles = a.nseg > 0 ? a.ntiles : (int)((a.fid_end - a.fid_begin + BLOCK - 1) / BLOCK);
+  const long long base = tile_base(a.fid_begin);  // tiles start on a 32-fid boundary (see first_fid)
+  const int ntiles = a.nseg > 0 ? a.ntiles : (int)((a.fid_end - base + BLOCK - 1) / BLOCK);
   int seg = 0;
   auto node_of = [&](int tile, int& k) -> long long {  // fid of this thread in `tile`, or -1
     if (a.nseg == 0) {
-      const long long f = a.fid_begin + (long long)tile * BLOCK + threadIdx.x;
-      return f < a.fid_end ? f : -1;
+      const long long f = base + (long long)tile * BLOCK + threadIdx.x;
+      return (f >= a.fid_begin && f < a.fid_end) ? f : -1;
     }
     while (tile >= a.tile_cum[k + 1]) ++k;  // tiles are visited in increasing order
     const long long f = a.seg_begin[k] + (long long)(tile - a.tile_cum[k]) * BLOCK + threadIdx.x;
@@ -210,8 +214,16 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
     static_for<1, NV>([&](auto Lc) {
       constexpr int L = decltype(Lc)::value;
       int fp;
+#if LBG_MP_EXP == 2   // diagnostic: no lookups, gathers hit the node's own line
+      fp = fid;
+      const int gp = fid;
+#elif LBG_MP_EXP == 1  // diagnostic: lookups kept, gathers hit the node's own line
+      const bool fl = lookup(geo, g + offset_plus<L>(nb), fp);
+      const int gp = fid + ((fp >> 30) & 1) + (fl ? 0 : ((fp >> 29) & 1));
+#else
       const bool fl = lookup(geo, g + offset_plus<L>(nb), fp);
       const int gp = fl ? fp : fid;
+#endif
       ax = ax + a.Pnow[gp] * q[L - 1];
       ay = ay + a.Pnow[nfa + gp] * q[L - 1];
       az = az + a.Pnow[2 * nfa + gp] * q[L - 1];
