@@ -171,6 +171,9 @@ struct lbg_handle_s {
   int ads = 0;
   int mp_bad = 0;
   double* q = nullptr;
+  uint32_t* nbt01 = nullptr;  // Phase-B neighbour table (lbg_internal.h NBT_*): words 0,1 in the spare array of f[0],
+  uint32_t* nbt27 = nullptr;  // words 2..7 in the three spare arrays of f[1]
+  int mp_use_nbt = 1;         // off on narrow lattices, where every warp holds nodes of the periodic x seam
   double* s = nullptr;
   double* P[2] = {nullptr, nullptr};
   double* A[2] = {nullptr, nullptr};
@@ -410,6 +413,7 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   h->geo.lx = lx;
   h->geo.ly = ly;
   h->geo.plane = (int)plane;
+  set_div_magic(h->geo);
   h->geo.nzl = nzl;
   h->geo.zwrap = zwrap ? 1 : 0;
   h->lz_global = lz_global;
@@ -1555,6 +1559,15 @@ int lbg_mp_init(lbg_handle h, double Db, double ka, double kd, const double f_ex
   h->P[1] = h->f[1] + 7 * g.nfa;
   h->A[0] = h->f[1] + 10 * g.nfa;
   h->A[1] = h->f[1] + 13 * g.nfa;
+  h->nbt01 = reinterpret_cast<uint32_t*>(h->f[0] + 18 * g.nfa);
+  h->nbt27 = reinterpret_cast<uint32_t*>(h->f[1] + 16 * g.nfa);
+  // Measured (profiles/variants_r3.txt): the table pays off on porous lattices (-13 % on cfg5w, -7 % on cfg3);
+  // on an all-fluid lattice the rank lookups are perfectly coalesced and cost no more than the table's
+  // 28 extra bytes per node; and a warp spans 32 fluid nodes of a row, so with fewer than ~8 warps per
+  // row the seam nodes' slow path dominates.
+  const double phi = (double)h->n_fluid / (double)(h->nown > 0 ? h->nown : 1);
+  h->mp_use_nbt = ((double)g.lx * phi >= 256.0 && phi < 0.95) ? 1 : 0;
+  if (const char* e = std::getenv("LBG_MP_NBT")) h->mp_use_nbt = std::atoi(e) ? 1 : 0;
   CK(cudaMemsetAsync(h->f[1], 0, 19 * nb, h->st));
   CK(cudaMemsetAsync(h->mp_err, 0, sizeof(int), h->st));
   CK(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
@@ -1563,6 +1576,8 @@ int lbg_mp_init(lbg_handle h, double Db, double ka, double kd, const double f_ex
   a.k = h->k;
   a.mom = h->mom;
   a.q = h->q;
+  a.nbt01 = h->nbt01;
+  a.nbt27 = h->nbt27;
   a.s = h->s;
   a.P0 = h->P[0];
   a.fid_begin = own_begin(h);
@@ -1648,6 +1663,9 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
       MPArgs a{};
       a.geo = g;
       a.q = h->q;
+      a.nbt01 = h->nbt01;
+      a.nbt27 = h->nbt27;
+      a.use_nbt = h->mp_use_nbt;
       a.s = h->s;
       a.Pnow = h->P[pc];
       a.Pnext = h->P[1 - pc];

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(BLOCK) build_gidx_kernel(Geo geo, long long nd
     const int g = (int)gg;
     int fid;
     if (!lookup(geo, g, fid)) continue;
-    const int p = g / geo.plane;
+    const int p = fast_div(g, geo.mul_plane, geo.sh_plane);
     uint32_t v = (uint32_t)g;
     if (p >= 1 && p <= geo.nzl && node_interfacial(geo, g, true)) v |= GIDX_INTERFACIAL;
     gidx[fid] = v;

@@ -21,10 +21,15 @@ struct Nb {
   int oxm, oxp, oym, oyp, ozm, ozp;
 };
 
+// floor(g / d) for 0 <= g < 2^31 with the multiplier of div_magic (lbg_internal.h)
+__device__ __forceinline__ int fast_div(int g, uint32_t mul, int sh) {
+  return (int)(((unsigned long long)(uint32_t)g * mul) >> sh);
+}
+
 __device__ __forceinline__ Nb neighbours(const Geo& geo, int g) {
-  const int p = g / geo.plane;
+  const int p = fast_div(g, geo.mul_plane, geo.sh_plane);
   const int rem = g - p * geo.plane;
-  const int y = rem / geo.lx;
+  const int y = fast_div(rem, geo.mul_lx, geo.sh_lx);
   const int x = rem - y * geo.lx;
   Nb nb;
   nb.oxm = (x == 0) ? (geo.lx - 1) : -1;

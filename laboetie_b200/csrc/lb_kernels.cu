@@ -16,6 +16,9 @@
 // the driver changes the force after a convergence event.
 #include "lb_node.cuh"
 
+#ifndef LBG_PULL_FENCE
+#define LBG_PULL_FENCE 0  // measured neutral to -1 % (profiles/variants_r3.txt): the kernel runs at the HBM rate of its access shape either way
+#endif
 #ifndef LBG_LOADMODE
 #define LBG_LOADMODE 1  // population loads: 0 default, 1 .cg (L2 only), 2 .cs (streaming); measured in profiles/
 #endif
@@ -37,20 +40,33 @@ __device__ __forceinline__ double ld_pop(const double* p) {
 
 // n(t)(r,·) by pull with halfway bounce-back.  The source of direction L is node r - c_L = r + c_inv(L);
 // if it is solid the population comes back from the node's own opposite slot.
+// Two phases: first all 18 rank lookups are resolved into (array, index) pairs, then the 19 population
+// loads are issued back to back.  A warp has few scoreboards: a lookup word that is consumed after the
+// first population loads were issued would wait for those DRAM loads too (one exposed latency more).
 __device__ __forceinline__ void pull(const Geo& geo, const double* __restrict__ fin, int fid, int g, const Nb& nb,
                                      double (&n)[NV]) {
   const long long nfa = geo.nfa;
-  static_for<0, NV>([&](auto Lc) {
+  int idx[NV];
+  uint32_t fluid = 0;
+  static_for<1, NV>([&](auto Lc) {
     constexpr int L = decltype(Lc)::value;
-    if constexpr (L == 0) {
-      n[0] = ld_pop(fin + fid);
-    } else {
-      int fsrc;
-      const bool src_fluid = lookup(geo, g + offset_plus<inv(L)>(nb), fsrc);
-      const int idx = src_fluid ? fsrc : fid;
-      const int arr = src_fluid ? L : inv(L);
-      n[L] = ld_pop(fin + (long long)arr * nfa + idx);
-    }
+    int fsrc;
+    const bool src_fluid = lookup(geo, g + offset_plus<inv(L)>(nb), fsrc);
+    idx[L] = src_fluid ? fsrc : fid;
+    fluid |= (src_fluid ? 1u : 0u) << L;
+  });
+#if LBG_PULL_FENCE
+  // make every population address depend on every lookup (geo.zero is 0 at run time), so that the
+  // scheduler cannot sink a lookup below the first population load
+  uint32_t any = fluid;
+  static_for<1, NV>([&](auto Lc) { any |= (uint32_t)idx[decltype(Lc)::value]; });
+  fin += (any & (uint32_t)geo.zero);
+#endif
+  n[0] = ld_pop(fin + fid);
+  static_for<1, NV>([&](auto Lc) {
+    constexpr int L = decltype(Lc)::value;
+    const int arr = ((fluid >> L) & 1u) ? L : inv(L);
+    n[L] = ld_pop(fin + (long long)arr * nfa + idx[L]);
   });
 }
 

@@ -35,7 +35,28 @@ struct Geo {
   long long nfa;          // stride of every per-fluid-node array (multiple of 32 elements)
   const uint2* words;     // {bits, rank} per 32 dense nodes over planes 0..nzl+1
   const uint32_t* gidx;   // per fid: dense index, bit 31 = interfacial
+  // g / plane and g / lx for 0 <= g < 2^31 as (g * mul) >> sh  (set_div_magic; exact, see there)
+  uint32_t mul_plane, mul_lx;
+  int sh_plane, sh_lx;
+  int zero;               // always 0, unknown to the compiler: lets a kernel make one value depend on others (issue order)
 };
+
+// Round-up multiplier for an exact unsigned division of 31-bit dividends (Granlund & Montgomery):
+// with l = ceil(log2 d) and m = ceil(2^(31+l) / d), floor(g / d) == (g * m) >> (31 + l) for all
+// 0 <= g < 2^31, and m fits in 32 bits.
+inline void div_magic(int d, uint32_t* mul, int* sh) {
+  int l = 0;
+  while ((1LL << l) < (long long)d) ++l;
+  const unsigned __int128 one = 1;
+  const unsigned __int128 m = ((one << (31 + l)) + (unsigned)d - 1) / (unsigned)d;
+  *mul = (uint32_t)m;
+  *sh = 31 + l;
+}
+
+inline void set_div_magic(Geo& g) {
+  div_magic(g.plane, &g.mul_plane, &g.sh_plane);
+  div_magic(g.lx, &g.mul_lx, &g.sh_lx);
+}
 
 // Device-side control block: lets a batch of step kernels stop itself at the
 // reference's exit step without a host round trip per step.
@@ -106,7 +127,26 @@ struct MPInitArgs {
   int ads;
   double* partial;     // per block: vacf0 x,y,z
   int* err;            // set if the remaining fraction < eps somewhere
+  uint32_t* nbt01;     // neighbour table words 0,1 (stride nfa), see NBT_* below
+  uint32_t* nbt27;     // words 2..7 (stride nfa)
 };
+
+// Phase-B neighbour table: the flow AND the geometry are frozen, so the fluid ids of a node's
+// neighbours are static too.  Eight 32-bit words per fluid node, one per neighbouring row
+// (dy,dz) != (0,0):  bits 0..29 = rank position c of the row's centre node (x, y+dy, z+dz) (its fid
+// if it is fluid), bit 31 = centre is fluid.  The x-neighbours of a row follow without a lookup:
+// fid(x+1) = c + centre_fluid, fid(x-1) = c - 1 (if that node is solid the index is a harmless in-range
+// one: its link probability q is 0).  Word 0 bit 30 = "slow": the node sits on the periodic x seam (or
+// an index would leave the arrays) and resolves its neighbours through the rank structure instead
+// (word 2 then holds its dense index g); word 1 bit 30 = interfacial.  32 bytes per node replace gidx (4 bytes) and 18 rank lookups per step.
+constexpr uint32_t NBT_FID_MASK = 0x3fffffffu;
+constexpr uint32_t NBT_FLAG = 0x40000000u;       // word 0: slow, word 1: interfacial
+constexpr uint32_t NBT_CENTRE_FLUID = 0x80000000u;
+// row index of a direction's (cy, cz); -1 for the node's own row
+__host__ __device__ constexpr int nbt_row(int cy, int cz) {
+  return cz == 0 ? (cy > 0 ? 0 : (cy < 0 ? 1 : -1))
+                 : (cz > 0 ? (cy == 0 ? 2 : (cy > 0 ? 4 : 5)) : (cy == 0 ? 3 : (cy > 0 ? 6 : 7)));
+}
 
 struct MPArgs {
   Geo geo;
@@ -126,6 +166,9 @@ struct MPArgs {
   int check_slot;       // evaluate the convergence criterion on this (complete, global) slot, or -1
   double lim;           // 1/(2 lx ly lz / Db)
   Ctrl* ctrl;
+  const uint32_t* nbt01;  // neighbour table (see NBT_*), words 0,1 and 2..7
+  const uint32_t* nbt27;
+  int use_nbt;            // 0: resolve neighbours through the rank structure (narrow lattices: every warp has seam nodes)
   // optional strip order (see SegTable): nseg == 0 means plain fid order over [fid_begin, fid_end)
   int nseg, ntiles;
   const int* tile_cum;          // nseg + 1: tiles before segment k

@@ -19,8 +19,8 @@
 // overwritten every step (solid nodes own no storage).
 #include "lattice.cuh"
 
-#ifndef LBG_MP_EXP
-#define LBG_MP_EXP 0
+#ifndef LBG_MP_FENCE
+#define LBG_MP_FENCE 1
 #endif
 #ifndef LBG_MP_MINB
 #define LBG_MP_MINB 2
@@ -87,12 +87,21 @@ __global__ void __launch_bounds__(BLOCK) mp_init_kernel(const __grid_constant__ 
     const double tz = a.mom[3 * nfa + fid] + a.f[2];
     double frac = 1.0, usx = 0.0, usy = 0.0, usz = 0.0;
     double px = 0.0, py = 0.0, pz = 0.0;
+    uint32_t nbw[8];
+    // slow: on the periodic x seam, or a derived index (c - 1, c + 1, fid +- 1) would leave [0, nfa)
+    bool slow = (nb.oxm != -1) || (nb.oxp != 1) || fid < 1 || fid + 1 >= nfa;
     static_for<1, NV>([&](auto Lc) {
       constexpr int L = decltype(Lc)::value;
       constexpr int LI = inv(L);
       double q = 0.0;
       int fp;
-      if (lookup(geo, g + offset_plus<L>(nb), fp)) {  // neighbour r + c_L is fluid
+      const bool fluid_nb = lookup(geo, g + offset_plus<L>(nb), fp);
+      if constexpr (cx(L) == 0) {  // centre node of a neighbouring row
+        constexpr int R = nbt_row(cy(L), cz(L));
+        nbw[R] = (uint32_t)fp | (fluid_nb ? NBT_CENTRE_FLUID : 0u);
+        slow = slow || fp < 1 || (long long)fp + 1 >= nfa;
+      }
+      if (fluid_nb) {  // neighbour r + c_L is fluid
         const double sp = scattprop<L>(a.k, a.lambda_w, rho, tx, ty, tz);
         frac = frac - sp;
         if constexpr (cx(L) > 0) usx = usx + sp;
@@ -123,6 +132,14 @@ __global__ void __launch_bounds__(BLOCK) mp_init_kernel(const __grid_constant__ 
     });
     if (a.ads && (gi & GIDX_INTERFACIAL)) frac = frac - a.ka;  // :240
     if (frac < eps) bad = true;                               // :249
+    if (slow) {  // such a node resolves all its neighbours through the rank structure: it needs g, not the row centres
+      nbw[0] = NBT_FLAG;
+      nbw[2] = (uint32_t)g;
+    }
+    if (gi & GIDX_INTERFACIAL) nbw[1] |= NBT_FLAG;
+    a.nbt01[fid] = nbw[0];
+    a.nbt01[nfa + fid] = nbw[1];
+    for (int r = 2; r < 8; ++r) a.nbt27[(long long)(r - 2) * nfa + fid] = nbw[r];
     a.s[fid] = frac;
     a.s[nfa + fid] = usx;
     a.s[2 * nfa + fid] = usy;
@@ -145,6 +162,8 @@ __global__ void __launch_bounds__(BLOCK) mp_init_kernel(const __grid_constant__ 
 // P are streamed in first (25 independent loads in flight), then the 18 neighbour gathers are
 // issued without conditions -- a solid neighbour is replaced by the node itself and its q is 0
 // (mp_init stores 0 there), so it adds exactly 0.
+// NBT: neighbour fluid ids from the static table (lbg_internal.h NBT_*) instead of 18 rank lookups per node.
+template <bool NBT>
 __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __grid_constant__ MPArgs a) {
   __shared__ double sh[3][BLOCK / 32];
   __shared__ int s_flag;
@@ -184,17 +203,72 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
     return f < a.seg_end[k] ? f : -1;
   };
   long long f_next = blockIdx.x < ntiles ? node_of(blockIdx.x, seg) : -1;
-  uint32_t gi_next = f_next >= 0 ? __ldg(geo.gidx + f_next) : 0u;
+  // neighbour-table words (NBT) or the dense index (gidx) of the next tile are fetched one iteration
+  // ahead: the gathers depend on them
+  uint32_t w_next[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto load_words = [&](long long f) {
+    if constexpr (NBT) {
+      w_next[0] = __ldcs(a.nbt01 + f);
+      w_next[1] = __ldcs(a.nbt01 + nfa + f);
+#pragma unroll
+      for (int r = 2; r < 8; ++r) w_next[r] = __ldcs(a.nbt27 + (long long)(r - 2) * nfa + f);
+    } else {
+      w_next[0] = __ldg(geo.gidx + f);
+    }
+  };
+  if (f_next >= 0) load_words(f_next);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long ff = f_next;
-    const uint32_t gi = gi_next;
     const int tn = tile + gridDim.x;
+    uint32_t w[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) w[r] = w_next[r];
     f_next = tn < ntiles ? node_of(tn, seg) : -1;
-    if (f_next >= 0) gi_next = __ldg(geo.gidx + f_next);
+    if (f_next >= 0) load_words(f_next);
     if (ff < 0) continue;
     const int fid = (int)ff;
-    const int g = (int)(gi & GIDX_MASK);
-    const bool adsorbing = a.ads && (gi & GIDX_INTERFACIAL);
+    const bool adsorbing = a.ads && (NBT ? (w[1] & NBT_FLAG) : (w[0] & GIDX_INTERFACIAL));
+    // fluid ids of the 18 neighbours (a solid one -> any in-range id: its q is 0 and adds exactly 0)
+    int gp[NV];
+    const double* Pn = a.Pnow;
+    auto resolve_by_lookup = [&](int g) {
+      // Two phases, as in the LB pull: resolve all 18 rank lookups first, then gather.  geo.zero is 0
+      // at run time and makes every gather address depend on every lookup, which pins that order in
+      // the schedule (a lookup word consumed after the first gathers were issued would share a
+      // scoreboard with them and wait for their latency as well).
+      const Nb nb = neighbours(geo, g);
+      uint32_t any = 0;
+      static_for<1, NV>([&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        int fp;
+        const bool fl = lookup(geo, g + offset_plus<L>(nb), fp);
+        gp[L] = fl ? fp : fid;
+        any |= (uint32_t)gp[L];
+      });
+#if LBG_MP_FENCE
+      Pn = a.Pnow + (any & (uint32_t)geo.zero);
+#endif
+    };
+    if constexpr (NBT) {
+      if (w[0] & NBT_FLAG) {  // periodic x seam (few nodes): through the rank structure, word 2 holds g
+        resolve_by_lookup((int)(w[2] & GIDX_MASK));
+      } else {
+        static_for<1, NV>([&](auto Lc) {
+          constexpr int L = decltype(Lc)::value;
+          constexpr int R = nbt_row(cy(L), cz(L));
+          if constexpr (R < 0) {
+            gp[L] = fid + cx(L);
+          } else {
+            const int c = (int)(w[R] & NBT_FID_MASK);
+            if constexpr (cx(L) == 0) gp[L] = c;
+            else if constexpr (cx(L) > 0) gp[L] = c + (int)(w[R] >> 31);
+            else gp[L] = c - 1;
+          }
+        });
+      }
+    } else {
+      resolve_by_lookup((int)(w[0] & GIDX_MASK));
+    }
     double q[NV - 1];
     static_for<1, NV>([&](auto Lc) {
       constexpr int L = decltype(Lc)::value;
@@ -209,24 +283,13 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
       sy = a.Anow[nfa + fid];
       sz = a.Anow[2 * nfa + fid];
     }
-    const Nb nb = neighbours(geo, g);
     double ax = 0.0, ay = 0.0, az = 0.0;  // Propagated_Quantity(:,r,next) is always 0 on entry
     static_for<1, NV>([&](auto Lc) {
       constexpr int L = decltype(Lc)::value;
-      int fp;
-#if LBG_MP_EXP == 2   // diagnostic: no lookups, gathers hit the node's own line
-      fp = fid;
-      const int gp = fid;
-#elif LBG_MP_EXP == 1  // diagnostic: lookups kept, gathers hit the node's own line
-      const bool fl = lookup(geo, g + offset_plus<L>(nb), fp);
-      const int gp = fid + ((fp >> 30) & 1) + (fl ? 0 : ((fp >> 29) & 1));
-#else
-      const bool fl = lookup(geo, g + offset_plus<L>(nb), fp);
-      const int gp = fl ? fp : fid;
-#endif
-      ax = ax + a.Pnow[gp] * q[L - 1];
-      ay = ay + a.Pnow[nfa + gp] * q[L - 1];
-      az = az + a.Pnow[2 * nfa + gp] * q[L - 1];
+      const double* p = Pn + gp[L];
+      ax = ax + p[0] * q[L - 1];
+      ay = ay + p[nfa] * q[L - 1];
+      az = az + p[2 * nfa] * q[L - 1];
     });
     vx += px * usx;  // vacf(:,now) += P(:,r,now)*u_star   (:232)
     vy += py * usy;
@@ -303,19 +366,24 @@ int launch_mp_init(const MPInitArgs& a, int grid, cudaStream_t st) {
 }
 
 int launch_mp_step(const MPArgs& a, int grid, cudaStream_t st) {
+  int gr;
   if (a.nseg > 0) {
     if (a.ntiles <= 0) return 0;
-    mp_step_kernel<<<a.ntiles < grid ? a.ntiles : grid, BLOCK, 0, st>>>(a);
-    return 1;
+    gr = a.ntiles < grid ? a.ntiles : grid;
+  } else {
+    if (a.fid_end <= a.fid_begin) return 0;
+    gr = clamp_grid(a.fid_end - a.fid_begin, grid);
   }
-  if (a.fid_end <= a.fid_begin) return 0;
-  mp_step_kernel<<<clamp_grid(a.fid_end - a.fid_begin, grid), BLOCK, 0, st>>>(a);
+  if (a.use_nbt) mp_step_kernel<true><<<gr, BLOCK, 0, st>>>(a);
+  else mp_step_kernel<false><<<gr, BLOCK, 0, st>>>(a);
   return 1;
 }
 
 int occupancy_grid_mp(int sm_count) {
-  int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp_step_kernel, BLOCK, 0);
+  int per_sm = 0, per_sm2 = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp_step_kernel<true>, BLOCK, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, mp_step_kernel<false>, BLOCK, 0);
+  if (per_sm2 < per_sm) per_sm = per_sm2;
   if (per_sm < 1) per_sm = 1;
   return sm_count * per_sm;
 }

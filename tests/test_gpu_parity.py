@@ -233,10 +233,18 @@ def test_tuto_config1_flow_and_tracers():
         assert (np.abs(d["vacf"] - g["vacf"]) <= RTOL * scale).all()
 
 
+MP_GEOMS = GEOMS[:9] + [GEOMS[14]]
+
+
+@pytest.mark.parametrize("nbt", ["0", "1"], ids=["rank-lookups", "neighbour-table"])
 @pytest.mark.parametrize("ka,kd", [(0.1, 0.01), (0.0, 0.0), (0.05, 0.0)])
-@pytest.mark.parametrize("name,mk", GEOMS[:9], ids=[g[0] for g in GEOMS[:9]])
-def test_moment_propagation_bit_exact(name, mk, ka, kd):
+@pytest.mark.parametrize("name,mk", MP_GEOMS, ids=[g[0] for g in MP_GEOMS])
+def test_moment_propagation_bit_exact(name, mk, ka, kd, nbt, monkeypatch):
+    """Both ways the propagate kernel finds a node's neighbours -- 18 rank lookups, or the static
+    neighbour table with its periodic-x-seam fallback (the library picks by lattice shape; forced
+    here) -- must give the oracle's P, Pads bit for bit."""
     lb = _gpu()
+    monkeypatch.setenv("LBG_MP_NBT", nbt)
     nat = mk()
     itf = O.detect_interfacial(nat)
     f = [1e-4, 2e-4, -1e-4]

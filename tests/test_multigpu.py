@@ -43,12 +43,13 @@ def _run_ranks(nranks, fn):
 
 @pytest.mark.parametrize("shape,nranks", [((16, 12, 21), 2), ((1, 9, 14), 2), ((33, 5, 8), 2), ((8, 8, 9), 4),
                                           ((6, 5, 10, "slit"), 2)])
-@pytest.mark.parametrize("tau", [1.0, 0.8])
-def test_slabs_match_single_gpu(shape, nranks, tau):
+@pytest.mark.parametrize("tau,nbt", [(1.0, "0"), (0.8, "1")])
+def test_slabs_match_single_gpu(shape, nranks, tau, nbt, monkeypatch):
     import laboetie_b200 as lb
     from laboetie_b200 import api, slab
     if _ndev() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
+    monkeypatch.setenv("LBG_MP_NBT", nbt)   # propagate kernel: rank lookups / static neighbour table (halo fids in the table)
     lx, ly, lz = shape[:3]
     nat = random_nature(lx, ly, lz, 0.25, 77)
     if len(shape) > 3:      # solid walls at both z ends: the halo planes across the ring seam hold no fluid node
