@@ -48,7 +48,7 @@ TAU = 1.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5w")
@@ -286,6 +286,8 @@ def run_ours(args):
         sim = make_sim()
         sim.lb_init(1.0)
         sim.lb_set_force_uniform(f_ext)
+        sim.sync()
+        t_setup = time.perf_counter() - t0   # create: H2D of the geometry, device allocations, numbering; initial state
         done, conv, hist = sim.lb_step(K, tau=TAU, check_every=1, target_error=-1.0)
         if bufs is not None:
             sim._ck(sim._L.lbg_lb_download_moments(sim._h, *bufs))
@@ -300,8 +302,8 @@ def run_ours(args):
         e2e = {"value": n_total * K / t_e2e / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": float(nat.nbytes * nranks) / K,
                "d2h_bytes_per_step": float((4 * 8 * own) * nranks) / K + 8 + 24,
-               "seconds": t_e2e,
-               "what": "create(H2D geometry)+lb_init+K LB steps(l2err history D2H)+moments D2H(pinned)+mp_init+K MP steps(vacf D2H); fixed costs amortised over K"}
+               "seconds": t_e2e, "setup_seconds": t_setup,
+               "what": "create(H2D geometry)+lb_init+K LB steps(l2err history D2H)+moments D2H(pinned)+mp_init+K MP steps(vacf D2H); fixed costs (setup_seconds, the moments read-back, mp_init) amortised over K"}
 
     # ---- the other BASELINE configurations that fit one GPU, device-resident numbers only (N=1) ------
     also = {}
@@ -353,7 +355,10 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "lb_step_kernel (pull stream + moments + collide)", "achieved": lb_gbs,
                      "peak": hbm, "unit": "GB/s", "frac": lb_gbs / hbm, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": b_lb,
-                     "mp_step_kernel": {"achieved": mp_gbs, "frac": mp_gbs / hbm, "algorithmic_bytes_per_launch": b_mp}},
+                     "mp_step_kernel": {"achieved": mp_gbs, "frac": mp_gbs / hbm, "algorithmic_bytes_per_launch": b_mp},
+                     # what a lattice-free kernel of the same access shape reaches (tools/microbench/streams.cu)
+                     "shape_yardstick": {"lb_pull_19_to_19_gbs": 5380.4, "mp_read_25_to_3_gbs": 6716.3,
+                                         "source": "profiles/streams_r3i.txt"}},
         "gpu_launches": int(l_lb + l_mp), "clocks": clocks,
     }
     if also:
@@ -367,7 +372,9 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
     if os.path.exists(tp):
         try:
-            line["roofline"]["traffic"] = json.load(open(tp)).get("lb_step_kernel_bytes_per_launch")
+            tr = json.load(open(tp))
+            line["roofline"]["traffic"] = tr.get("lb_step_kernel_bytes_per_launch")
+            line["roofline"]["mp_step_kernel"]["traffic"] = tr.get("mp_step_kernel_bytes_per_launch")
         except Exception:
             pass
     print(json.dumps(line))
