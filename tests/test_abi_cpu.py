@@ -88,3 +88,57 @@ def test_compensating_force_field_matches_oracle():
         driver.compensating_force_field(O.geometry(-1, 4, 5, 5), [1, 0, 0], 1)
     with pytest.raises(ValueError):
         driver.compensating_force_field(O.geometry(-1, 5, 5, 5), [1, 0, 0], 2)
+
+
+def test_host_side_index_helpers(tmp_path):
+    """div_magic (exact multiply-shift division used by every kernel to turn a dense node index into
+    (x, y, z)) and nbt_row (row numbering of the Phase-B neighbour table) are host-compilable: check
+    them with g++ against plain integer division / the D3Q19 table."""
+    import shutil
+    import subprocess
+    cuda_inc = "/usr/local/cuda/include"
+    if not (shutil.which("g++") and os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h"))):
+        pytest.skip("needs g++ and the CUDA headers")
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <cstdint>
+#include "lbg_internal.h"
+int main() {
+  long bad = 0;
+  const int ds[] = {1, 2, 3, 5, 7, 31, 32, 33, 50, 64, 100, 255, 256, 257, 1000, 1023, 1024, 1025, 2500, 4096, 65535,
+                    65536, 65537, 262144, 1048576, 1048577, 3000000, 16777216, 100000007, 1073741824, 2147483647};
+  for (int d : ds) {
+    uint32_t m; int sh;
+    lbg::div_magic(d, &m, &sh);
+    auto chk = [&](uint32_t g) { if ((uint32_t)(((unsigned long long)g * m) >> sh) != g / (uint32_t)d) ++bad; };
+    for (uint32_t g = 0; g < 300000; ++g) chk(g);
+    for (uint32_t g = 2147483647u; g > 2147483647u - 300000; --g) chk(g);
+    for (unsigned long long k = 1; k < 300000; ++k) {
+      const unsigned long long g = k * (unsigned)d;
+      if (g >= (1ull << 31)) break;
+      chk((uint32_t)g); chk((uint32_t)g - 1);
+    }
+    for (uint32_t g = 1; g < (1u << 31); g += 7919) chk(g);
+  }
+  // every direction with cx == 0 except the rest one is the centre of exactly one of the 8 rows
+  int seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int l = 1; l < d3q19::NV; ++l) {
+    const int r = lbg::nbt_row(d3q19::cy(l), d3q19::cz(l));
+    if (d3q19::cy(l) == 0 && d3q19::cz(l) == 0) { if (r != -1) ++bad; continue; }
+    if (r < 0 || r > 7) { ++bad; continue; }
+    if (d3q19::cx(l) == 0) ++seen[r];
+    // a row is shared by a direction and by the one with the same (cy, cz) only
+    for (int m = 1; m < d3q19::NV; ++m)
+      if ((lbg::nbt_row(d3q19::cy(m), d3q19::cz(m)) == r) != (d3q19::cy(m) == d3q19::cy(l) && d3q19::cz(m) == d3q19::cz(l))) ++bad;
+  }
+  for (int r = 0; r < 8; ++r) if (seen[r] != 1) ++bad;
+  printf("%ld\n", bad);
+  return bad != 0;
+}
+''')
+    exe = tmp_path / "t"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-D__host__=", "-D__device__=", "-I", cuda_inc,
+                           "-I", os.path.join(ROOT, "laboetie_b200", "csrc"), "-o", str(exe), str(src)])
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "0", out.stdout
