@@ -1561,12 +1561,11 @@ int lbg_mp_init(lbg_handle h, double Db, double ka, double kd, const double f_ex
   h->A[1] = h->f[1] + 13 * g.nfa;
   h->nbt01 = reinterpret_cast<uint32_t*>(h->f[0] + 18 * g.nfa);
   h->nbt27 = reinterpret_cast<uint32_t*>(h->f[1] + 16 * g.nfa);
-  // Measured (profiles/variants_r3.txt): the table pays off on porous lattices (-13 % on cfg5w, -7 % on cfg3);
-  // on an all-fluid lattice the rank lookups are perfectly coalesced and cost no more than the table's
-  // 28 extra bytes per node; and a warp spans 32 fluid nodes of a row, so with fewer than ~8 warps per
-  // row the seam nodes' slow path dominates.
+  // Measured (profiles/variants_r3.txt): the table pays off on porous lattices (-13 % on cfg5w; -7 % on the
+  // 256^3 BCC lattice, where 3 of 4 warps hold a seam node); on an all-fluid lattice the rank lookups
+  // are perfectly coalesced and cost no more than the table's 28 extra bytes per node.
   const double phi = (double)h->n_fluid / (double)(h->nown > 0 ? h->nown : 1);
-  h->mp_use_nbt = ((double)g.lx * phi >= 256.0 && phi < 0.95) ? 1 : 0;
+  h->mp_use_nbt = (g.lx >= 64 && phi < 0.95) ? 1 : 0;
   if (const char* e = std::getenv("LBG_MP_NBT")) h->mp_use_nbt = std::atoi(e) ? 1 : 0;
   CK(cudaMemsetAsync(h->f[1], 0, 19 * nb, h->st));
   CK(cudaMemsetAsync(h->mp_err, 0, sizeof(int), h->st));

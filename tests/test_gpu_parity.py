@@ -447,6 +447,45 @@ def test_full_size_config2_properties():
         assert np.isfinite(v).all()
 
 
+def test_full_size_config3_properties():
+    """BASELINE config 3 at full size (256^3 BCC spheres, adsorbing tracer): size-independent properties.
+    At this size the propagate kernel runs on its neighbour-table path by default."""
+    lb = _gpu()
+    L = 256
+    nat = O.geometry(3, L, L, L)
+    f = [1e-6, 0, 0]
+    nf = int((nat == 0).sum())
+    with lb.LaboetieGPU(nat) as sim:
+        assert sim.counts()[0] == nf
+        sim.lb_init(1.0)
+        sim.lb_set_force_uniform(f)
+        done, conv, h = sim.lb_step(60, check_every=1, target_error=-1.0)
+        assert done == 60 and np.isfinite(h).all() and (h >= 0).all()
+        rho, jx, jy, jz = sim.lb_moments()
+        assert (rho[nat == 1] == 0).all() and (jx[nat == 1] == 0).all()
+        assert abs(rho.sum() - nf) <= 1e-12 * nf                         # mass conservation
+        # the BCC cell is symmetric under y <-> z, and so is the forcing along x
+        tol = 1e-10 * np.abs(jx).max()   # the l-ordered sums treat y and z in a different order: rounding only
+        assert np.allclose(jx, jx.transpose(1, 0, 2), rtol=1e-9, atol=tol)
+        assert np.allclose(jy, jz.transpose(1, 0, 2), rtol=1e-9, atol=tol)
+        assert jx.sum() > 0
+        # mirror planes of the cell: total transverse flux vanishes up to rounding
+        assert abs(jy.sum()) <= 1e-9 * jx.sum() and abs(jz.sum()) <= 1e-9 * jx.sum()
+        v0 = sim.mp_init(0.01, 0.1, 0.01, f)
+        P0, A0 = sim.mp_download()
+        assert (A0 == 0).all() and (P0[nat == 1] == 0).all()
+        tot0 = P0.sum(axis=(0, 1, 2))
+        done, conv, v = sim.mp_step(40)
+        assert done == 40 and np.isfinite(v).all()
+        P, A = sim.mp_download()
+        tot = (P + A).sum(axis=(0, 1, 2))
+        assert np.allclose(tot, tot0, rtol=0, atol=1e-11 * np.abs(P0).sum())   # sum(P + Pads) is conserved
+        assert (P[nat == 1] == 0).all() and (A[itf_not(nat)] == 0).all()
+        assert (A[~itf_not(nat)] != 0).any()
+        # vacf decays from vacf(0) > 0 along every axis (diffusive tracer)
+        assert (v0 > 0).all() and (np.abs(v[-1]) < v0).all()
+
+
 def itf_not(nat):
     itf = O.detect_interfacial(nat)
     return ~((itf == 1) & (nat == 0))
