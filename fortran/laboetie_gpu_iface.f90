@@ -15,7 +15,7 @@ module laboetie_gpu
   public :: lbg_get_interfacial, lbg_get_counts
   public :: lbg_lb_set_in_place, lbg_lb_init, lbg_lb_upload, lbg_lb_set_force_uniform, lbg_lb_set_force_field, lbg_lb_step, lbg_lb_time
   public :: lbg_lb_download_moments, lbg_lb_download_populations, lbg_lb_profiles, lbg_lb_total_flux, lbg_lb_probe
-  public :: lbg_mp_init, lbg_mp_step, lbg_mp_download, lbg_sync, lbg_status_message
+  public :: lbg_mp_init, lbg_mp_init_from_moments, lbg_mp_step, lbg_mp_download, lbg_sync, lbg_status_message
 
   integer(c_int), parameter, public :: LBG_OK = 0
   integer(c_int), parameter, public :: LBG_ERR_NEGATIVE_POPULATION = 1   ! equilibration.f90:248
@@ -144,6 +144,16 @@ module laboetie_gpu
     integer(c_int) function lbg_mp_init(h, Db, ka, kd, f_ext, vacf0) bind(C, name="lbg_mp_init")
       import :: c_ptr, c_int, c_double
       type(c_ptr), value :: h
+      real(c_double), value :: Db, ka, kd
+      real(c_double), intent(in) :: f_ext(3)
+      real(c_double), intent(out) :: vacf0(3)
+    end function
+    ! Phase B from the driver's own arrays (node%solventdensity, node%solventflux of drop_tracers.f90:63-105)
+    integer(c_int) function lbg_mp_init_from_moments(h, rho, jx, jy, jz, Db, ka, kd, f_ext, vacf0) &
+        bind(C, name="lbg_mp_init_from_moments")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      real(c_double), intent(in) :: rho(*), jx(*), jy(*), jz(*)
       real(c_double), value :: Db, ka, kd
       real(c_double), intent(in) :: f_ext(3)
       real(c_double), intent(out) :: vacf0(3)

@@ -154,6 +154,13 @@ int lbg_lb_probe(lbg_handle h, int i, int j, int k, double out[4]);
  * deallocates n at drop_tracers.f90:85). */
 int lbg_mp_init(lbg_handle h, double tracer_Db, double tracer_ka, double tracer_kd, const double f_ext[3],
                 double vacf0[3]);
+/* The same, from the driver's own arrays: drop_tracers.f90:63-105 reads density and momentum density
+ * from node%solventdensity / node%solventflux (written back at equilibration.f90:551-554), so a driver
+ * that restarts from saved fields, or that ran Phase A elsewhere, starts Phase B here without any
+ * Lattice-Boltzmann state on the device.  rho, jx, jy, jz: (lx,ly,lz) arrays, i fastest (own planes). */
+int lbg_mp_init_from_moments(lbg_handle h, const double* rho, const double* jx, const double* jy, const double* jz,
+                             double tracer_Db, double tracer_ka, double tracer_kd, const double f_ext[3],
+                             double vacf0[3]);
 /* Up to nsteps calls of propagate (module_moment_propagation.f90:164-289).
  * vacf (may be NULL) receives vacf(:,now) of each executed step, 3 per step.
  * Returns after the first step `it` (counted from lbg_mp_init) with

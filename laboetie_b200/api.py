@@ -27,7 +27,7 @@ SYMBOLS = [
     "lbg_create", "lbg_create_slab", "lbg_create_geometry", "lbg_get_nature", "lbg_destroy", "lbg_comm_unique_id", "lbg_comm_init", "lbg_get_interfacial",
     "lbg_get_counts", "lbg_lb_set_in_place", "lbg_lb_init", "lbg_lb_upload", "lbg_lb_set_force_uniform", "lbg_lb_set_force_field",
     "lbg_lb_step", "lbg_lb_time", "lbg_lb_download_moments", "lbg_lb_download_populations", "lbg_lb_profiles",
-    "lbg_lb_total_flux", "lbg_lb_probe", "lbg_mp_init", "lbg_mp_step", "lbg_mp_download", "lbg_timer_start",
+    "lbg_lb_total_flux", "lbg_lb_probe", "lbg_mp_init", "lbg_mp_init_from_moments", "lbg_mp_step", "lbg_mp_download", "lbg_timer_start",
     "lbg_timer_stop", "lbg_launch_count", "lbg_sync",
 ]
 
@@ -85,6 +85,7 @@ def load_library():
     L.lbg_lb_total_flux.argtypes = [P, f64]
     L.lbg_lb_probe.argtypes = [P, I, I, I, f64]
     L.lbg_mp_init.argtypes = [P, D, D, D, C.POINTER(D * 3), f64]
+    L.lbg_mp_init_from_moments.argtypes = [P, f64, f64, f64, f64, D, D, D, C.POINTER(D * 3), f64]
     L.lbg_mp_step.argtypes = [P, I, P, C.POINTER(I), C.POINTER(I)]
     L.lbg_mp_download.argtypes = [P, P, P]
     L.lbg_timer_start.argtypes = [P]
@@ -276,6 +277,16 @@ class LaboetieGPU:
     def mp_init(self, Db, ka, kd, f_ext):
         v0 = np.zeros(3)
         self._ck(self._L.lbg_mp_init(self._h, Db, ka, kd, C.byref((C.c_double * 3)(*[float(v) for v in f_ext])), v0))
+        return v0
+
+    def mp_init_from_moments(self, rho, jx, jy, jz, Db, ka, kd, f_ext):
+        """Phase B from the driver's own density / momentum arrays (shape (nzl, ly, lx)); no LB state needed."""
+        v0 = np.zeros(3)
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (rho, jx, jy, jz)]
+        for a in arrs:
+            assert a.shape == (self.nzl, self.ly, self.lx), a.shape
+        self._ck(self._L.lbg_mp_init_from_moments(self._h, *arrs, Db, ka, kd,
+                                                  C.byref((C.c_double * 3)(*[float(v) for v in f_ext])), v0))
         return v0
 
     def mp_step(self, nsteps, want_history=True):

@@ -1515,14 +1515,25 @@ int lbg_lb_probe(lbg_handle h, int i, int j, int k, double out[4]) {
 }
 
 // --------------------------------------------------------------------------- Phase B
-int lbg_mp_init(lbg_handle h, double Db, double ka, double kd, const double f_ext[3], double vacf0[3]) {
+// rho_host != NULL: density and momentum density come from the driver's arrays (lbg_mp_init_from_moments)
+// instead of the resident Lattice-Boltzmann state.
+static int mp_init_impl(lbg_handle h, double Db, double ka, double kd, const double f_ext[3], double vacf0[3],
+                        const double* const host_mom[4]) {
   if (!h || !f_ext) return LBG_ERR_INVALID_ARG;
-  if (h->phase != PH_LB) return fail(h, LBG_ERR_STATE, "lbg_mp_init needs the Lattice-Boltzmann state (density, momentum)");
+  if (!host_mom && h->phase != PH_LB)
+    return fail(h, LBG_ERR_STATE, "lbg_mp_init needs the Lattice-Boltzmann state (density, momentum)");
   const double eps = std::numeric_limits<double>::epsilon();
   if (Db <= eps) return fail(h, LBG_ERR_TRACER_DB, lbg_status_string(LBG_ERR_TRACER_DB));       // drop_tracers.f90:89
   if (ka < -eps || kd < -eps) return fail(h, LBG_ERR_TRACER_KA_KD, lbg_status_string(LBG_ERR_TRACER_KA_KD));
   CK(cudaSetDevice(h->device));
-  RET(refresh_moments(h, nullptr));
+  if (host_mom) {
+    RET(wait_halo(h));
+    CK(cudaMemsetAsync(h->mom, 0, 4 * (size_t)h->geo.nfa * sizeof(double), h->st));
+    for (int c = 0; c < 4; ++c) RET(copy_own_to_device(h, h->mom + (long long)c * h->geo.nfa, host_mom[c]));
+    RET(ring_barrier(h));   // a neighbour's halo push of its moments must not be wiped by my memset
+  } else {
+    RET(refresh_moments(h, nullptr));
+  }
   const Geo& g = h->geo;
   if (h->nranks > 1) {
     const int all4[4] = {0, 1, 2, 3};
@@ -1625,6 +1636,17 @@ int lbg_mp_init(lbg_handle h, double Db, double ka, double kd, const double f_ex
   h->it = 0;
   h->pc = 0;
   return LBG_OK;
+}
+
+int lbg_mp_init(lbg_handle h, double Db, double ka, double kd, const double f_ext[3], double vacf0[3]) {
+  return mp_init_impl(h, Db, ka, kd, f_ext, vacf0, nullptr);
+}
+
+int lbg_mp_init_from_moments(lbg_handle h, const double* rho, const double* jx, const double* jy, const double* jz,
+                             double Db, double ka, double kd, const double f_ext[3], double vacf0[3]) {
+  if (!h || !rho || !jx || !jy || !jz) return LBG_ERR_INVALID_ARG;
+  const double* const m[4] = {rho, jx, jy, jz};
+  return mp_init_impl(h, Db, ka, kd, f_ext, vacf0, m);
 }
 
 int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* converged) {

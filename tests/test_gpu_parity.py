@@ -6,6 +6,8 @@ density, momentum, P, Pads, interfacial flags, l2err, exit step) are expected
 to be *bit-identical* and are tested with array_equal; cross-node sums (vacf,
 profiles, total flux) are tested at RTOL = 1e-12 relative to the field scale.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -303,6 +305,46 @@ def test_moment_propagation_strip_order(rows, monkeypatch):
         P, A = sim.mp_download()
         assert np.array_equal(P, mp.P[0]) and np.array_equal(A, mp.Pads[0])
         assert (np.abs(v - ref_v) <= RTOL * np.abs(mp.vacf0).max()).all()
+
+
+def test_phase_b_from_host_moments():
+    """lbg_mp_init_from_moments: Phase B started from the driver's density / momentum arrays (what
+    drop_tracers.f90:63-105 reads from node%solventdensity/solventflux) is bit-identical to Phase B started
+    from the resident Lattice-Boltzmann state, and to the oracle; no LB state is needed on that handle."""
+    lb = _gpu()
+    nat = random_nature(34, 6, 7, 0.3, 77)
+    itf = O.detect_interfacial(nat)
+    f = [2e-4, -1e-4, 3e-4]
+    st = O.LBState(nat, 1.0, 0.9)
+    st.set_force_uniform(f)
+    for _ in range(9):
+        st.step()
+    mp = O.MPState(nat, itf, st.rho, st.jx, st.jy, st.jz, f, 0.02, 0.08, 0.03)
+    ref_v = np.array([mp.propagate()[1] for _ in range(12)])
+    with lb.LaboetieGPU(nat) as a:
+        a.lb_init(1.0)
+        a.lb_set_force_uniform(f)
+        a.lb_step(9, tau=0.9, check_every=0)
+        rho, jx, jy, jz = a.lb_moments()
+        assert np.array_equal(rho, st.rho) and np.array_equal(jx, st.jx)
+        v0a = a.mp_init(0.02, 0.08, 0.03, f)
+        _, _, va = a.mp_step(12)
+        Pa, Aa = a.mp_download()
+    for nbt in ("0", "1"):
+        os.environ["LBG_MP_NBT"] = nbt
+        try:
+            with lb.LaboetieGPU(nat) as b:
+                v0b = b.mp_init_from_moments(rho, jx, jy, jz, 0.02, 0.08, 0.03, f)
+                _, _, vb = b.mp_step(12)
+                Pb, Ab = b.mp_download()
+                with pytest.raises(lb.LbgError):      # no Lattice-Boltzmann state on this handle
+                    b.lb_step(1)
+        finally:
+            del os.environ["LBG_MP_NBT"]
+        assert np.array_equal(v0a, v0b) and np.array_equal(va, vb)
+        assert np.array_equal(Pa, Pb) and np.array_equal(Aa, Ab)
+        assert np.array_equal(Pb, mp.P[0]) and np.array_equal(Ab, mp.Pads[0])
+        assert (np.abs(vb - ref_v) <= RTOL * np.abs(mp.vacf0).max()).all()
 
 
 def test_mp_convergence_step_matches():
