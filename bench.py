@@ -289,26 +289,35 @@ def run_ours(args):
             bufs = None
         barrier()
         t0 = time.perf_counter()
+        marks = [("start", t0)]
+        mark = lambda name: marks.append((name, time.perf_counter()))   # noqa: E731
         sim = make_sim()
+        mark("create")            # H2D of the geometry, device allocations, numbering
         sim.lb_init(1.0)
         sim.lb_set_force_uniform(f_ext)
         sim.sync()
-        t_setup = time.perf_counter() - t0   # create: H2D of the geometry, device allocations, numbering; initial state
+        mark("lb_init")
+        t_setup = time.perf_counter() - t0
         done, conv, hist = sim.lb_step(K, tau=TAU, check_every=1, target_error=-1.0)
+        mark("lb_steps")          # K steps, l2err history D2H
         if bufs is not None:
             sim._ck(sim._L.lbg_lb_download_moments(sim._h, *bufs))
         else:
             bufs = sim.lb_moments()
+        mark("moments_d2h")       # density and momentum density into pinned host arrays
         v0 = sim.mp_init(TRACER["Db"], TRACER["ka"], TRACER["kd"], f_ext)
+        mark("mp_init")
         done, conv, vac = sim.mp_step(K)
         sim.sync()
+        mark("mp_steps")          # K steps, vacf rows D2H
         t_e2e = allmax(time.perf_counter() - t0)
         sim.close()
+        phases = {b[0]: b[1] - a[1] for a, b in zip(marks, marks[1:])}
         own = nat[1:-1].size if nranks > 1 else nat.size
         e2e = {"value": n_total * K / t_e2e / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": float(nat.nbytes * nranks) / K,
                "d2h_bytes_per_step": float((4 * 8 * own) * nranks) / K + 8 + 24,
-               "seconds": t_e2e, "setup_seconds": t_setup,
+               "seconds": t_e2e, "setup_seconds": t_setup, "phase_seconds": phases,
                "what": "create(H2D geometry)+lb_init+K LB steps(l2err history D2H)+moments D2H(pinned)+mp_init+K MP steps(vacf D2H); fixed costs (setup_seconds, the moments read-back, mp_init) amortised over K"}
 
     # ---- the other BASELINE configurations that fit one GPU, device-resident numbers only (N=1) ------

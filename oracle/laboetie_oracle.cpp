@@ -12,7 +12,7 @@
 // reference routines listed below; its fidelity rests on (1) inspection
 // against the cited lines, (2) an independently written numpy restatement
 // (oracle/numpy_restatement.py) that must agree with it bit for bit, and
-// (3) the analytic invariants in tests/test_oracle_invariants.py.
+// (3) the analytic invariants in tests/test_oracle.py.
 //
 // Restated routines (file:line relative to /root/reference):
 //   src/module_lbmodel.f90:66-86,122-162     D3Q19 velocities, weights, inverse
