@@ -175,6 +175,13 @@ int lbg_timer_start(lbg_handle h);
 int lbg_timer_stop(lbg_handle h, float* milliseconds);
 /* number of kernels this library has launched on this handle */
 int lbg_launch_count(lbg_handle h, int64_t* launches);
+/* Which code path a handle runs (diagnostics for tests and bench lines; no reference counterpart).  Keys:
+ * "mp_neighbour_table" (Phase B resolves neighbours from its static table: 1, through rank lookups: 0),
+ * "lb_variant" (100*pipelined + 10*tiles-per-chunk-is-dynamic + blocks per SM of the Phase-A kernel),
+ * "in_place", "p2p" (peer-to-peer halos: 1, NCCL send/recv: 0), "ipc" (a neighbour's memory is mapped
+ * through CUDA IPC, i.e. one process per GPU), "nranks", "rank", "fluid_nodes_with_halo".
+ * Unknown key: LBG_ERR_INVALID_ARG. */
+int lbg_get_info(lbg_handle h, const char* key, int64_t* value);
 int lbg_sync(lbg_handle h);
 
 #ifdef __cplusplus

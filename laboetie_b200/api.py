@@ -28,7 +28,7 @@ SYMBOLS = [
     "lbg_get_counts", "lbg_lb_set_in_place", "lbg_lb_init", "lbg_lb_upload", "lbg_lb_set_force_uniform", "lbg_lb_set_force_field",
     "lbg_lb_step", "lbg_lb_time", "lbg_lb_download_moments", "lbg_lb_download_populations", "lbg_lb_profiles",
     "lbg_lb_total_flux", "lbg_lb_probe", "lbg_mp_init", "lbg_mp_init_from_moments", "lbg_mp_step", "lbg_mp_download", "lbg_timer_start",
-    "lbg_timer_stop", "lbg_launch_count", "lbg_sync",
+    "lbg_timer_stop", "lbg_launch_count", "lbg_get_info", "lbg_sync",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library():
     L.lbg_timer_start.argtypes = [P]
     L.lbg_timer_stop.argtypes = [P, C.POINTER(C.c_float)]
     L.lbg_launch_count.argtypes = [P, C.POINTER(C.c_int64)]
+    L.lbg_get_info.argtypes = [P, C.c_char_p, C.POINTER(C.c_int64)]
     L.lbg_sync.argtypes = [P]
     if L.lbg_abi_version() != 1:
         raise LbgError(7, "ABI version mismatch between api.py and liblaboetie_gpu.so")
@@ -196,6 +197,19 @@ class LaboetieGPU:
         self._ck(self._L.lbg_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def info(self, key):
+        """Which code path the handle runs (lbg_get_info): 'mp_neighbour_table', 'lb_variant', 'p2p', 'ipc', ..."""
+        v = C.c_int64()
+        self._ck(self._L.lbg_get_info(self._h, key.encode(), C.byref(v)))
+        return v.value
+
+    def _field(self, x, what, lead=()):
+        """C-contiguous fp64 array of exactly the slab's shape: the library reads nown values per array."""
+        a = np.ascontiguousarray(x, np.float64)
+        if a.shape != tuple(lead) + self.shape:
+            raise LbgError(7, f"{what}: shape {a.shape}, expected {tuple(lead) + self.shape}")
+        return a
+
     # -- geometry ---------------------------------------------------------
     def interfacial(self):
         out = np.zeros(self.shape, np.int8)
@@ -221,14 +235,14 @@ class LaboetieGPU:
         self._ck(self._L.lbg_lb_init(self._h, rho0))
 
     def lb_upload(self, n, rho, jx, jy, jz):
-        a = [np.ascontiguousarray(x, np.float64) for x in (n, rho, jx, jy, jz)]
+        a = [self._field(n, "lb_upload n", (19,))] + [self._field(x, "lb_upload moments") for x in (rho, jx, jy, jz)]
         self._ck(self._L.lbg_lb_upload(self._h, *a))
 
     def lb_set_force_uniform(self, f):
         self._ck(self._L.lbg_lb_set_force_uniform(self._h, C.byref((C.c_double * 3)(*[float(v) for v in f]))))
 
     def lb_set_force_field(self, fx, fy, fz):
-        a = [np.ascontiguousarray(x, np.float64) for x in (fx, fy, fz)]
+        a = [self._field(x, "lb_set_force_field") for x in (fx, fy, fz)]
         self._ck(self._L.lbg_lb_set_force_field(self._h, *a))
 
     def lb_step(self, nsteps, tau=1.0, check_every=1, target_error=1e-10, want_history=True):
@@ -282,9 +296,7 @@ class LaboetieGPU:
     def mp_init_from_moments(self, rho, jx, jy, jz, Db, ka, kd, f_ext):
         """Phase B from the driver's own density / momentum arrays (shape (nzl, ly, lx)); no LB state needed."""
         v0 = np.zeros(3)
-        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (rho, jx, jy, jz)]
-        for a in arrs:
-            assert a.shape == (self.nzl, self.ly, self.lx), a.shape
+        arrs = [self._field(a, "mp_init_from_moments") for a in (rho, jx, jy, jz)]
         self._ck(self._L.lbg_mp_init_from_moments(self._h, *arrs, Db, ka, kd,
                                                   C.byref((C.c_double * 3)(*[float(v) for v in f_ext])), v0))
         return v0

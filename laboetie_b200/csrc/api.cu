@@ -147,6 +147,8 @@ struct lbg_handle_s {
   d3q19::Consts k{};
   int grid_lb = 148, grid_mp = 148;
   int lb_minb = 2;  // register-allocation variant of the LB step kernel (see lb_kernels.cu)
+  int lb_pipe = 1;             // software-pipelined step kernel (lb_kernels.cu lb_step_pipe_kernel)
+  int lb_tpc = 0;              // tiles per chunk of the dynamic tile schedule of the Phase-A kernels (Geo::tpc; 0 = static)
   int64_t n_fluid = 0, n_if_fluid = 0;  // own planes
 
   Phase phase = PH_CREATED;
@@ -507,11 +509,21 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   CKB(cudaMalloc(&h->mom, 4 * nb));
   CKB(cudaMalloc(&h->jpp[0], 3 * nb));
   CKB(cudaMalloc(&h->jpp[1], 3 * nb));
-  const int maxgrid = h->grid_mp + 8;
-  CKB(cudaMalloc(&h->partial, 3 * (size_t)maxgrid * sizeof(double)));
-  // small slabs (latency / tail dominated) run the 3-blocks-per-SM variant (profiles/variants_r1f.txt)
+  CKB(cudaMalloc(&h->partial, 3 * (size_t)(h->grid_mp + 8) * sizeof(double)));
+  // Variant of the Phase-A step kernel (lb_kernels.cu), measured per workload in profiles/ab_r5a.txt:
+  //   large slabs: plain kernel, 3 CTAs per SM (80 registers), tiles handed out two at a time by an atomic
+  //                counter (cfg5w: 5.44 ms vs 5.70 ms for the static 2-CTA variant);
+  //   small slabs (launches of 70-350 us, tail dominated): two-stage software pipeline, 2 CTAs per SM, static
+  //                tile-stride schedule (cfg3: 0.330 vs 0.344 ms; cfg2: 0.068 vs 0.071 ms).
+  // LBG_LB_PIPE / LBG_LB_TPC / LBG_LB_MINB override for tuning runs.
+  const bool small = h->n_fluid < (8LL << 20);
+  h->lb_pipe = small ? 1 : 0;
+  h->lb_tpc = small ? 0 : 2;
+  h->lb_minb = small ? 2 : 3;
+  if (const char* e = std::getenv("LBG_LB_PIPE")) h->lb_pipe = std::atoi(e) ? 1 : 0;
+  if (const char* e = std::getenv("LBG_LB_TPC")) h->lb_tpc = std::atoi(e) > 0 ? std::atoi(e) : 0;
   if (const char* e = std::getenv("LBG_LB_MINB")) h->lb_minb = std::atoi(e) >= 3 ? 3 : 2;
-  else h->lb_minb = (h->n_fluid < (8LL << 20)) ? 3 : 2;
+  h->geo.tpc = h->lb_tpc;
   h->grid_lb = occupancy_grid_lb(h->sm_count, h->lb_minb);
   h->grid_aa = occupancy_grid_aa(h->sm_count);
 #undef CKB
@@ -662,6 +674,7 @@ int enqueue_lb_kernel(lbg_handle h, int fin, double tau, const ForceSel& fs, int
   a.prev_may_stop = fl.prev_may_stop;
   a.target = fl.target;
   a.ctrl = h->ctrl;
+  a.pipe = h->lb_pipe;
   const bool tau1 = (tau == 1.0);
   const std::vector<long long>& ps = h->pstart;
   const int nz = h->geo.nzl;
@@ -1683,6 +1696,7 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
       const long long it = h->it + 1 + i;
       MPArgs a{};
       a.geo = g;
+      a.geo.tpc = 0;
       a.q = h->q;
       a.nbt01 = h->nbt01;
       a.nbt27 = h->nbt27;
@@ -1814,6 +1828,21 @@ int lbg_timer_stop(lbg_handle h, float* ms) {
 int lbg_launch_count(lbg_handle h, int64_t* n) {
   if (!h || !n) return LBG_ERR_INVALID_ARG;
   *n = h->launches;
+  return LBG_OK;
+}
+
+int lbg_get_info(lbg_handle h, const char* key, int64_t* value) {
+  if (!h || !key || !value) return LBG_ERR_INVALID_ARG;
+  const std::string k(key);
+  if (k == "mp_neighbour_table") *value = h->mp_use_nbt;
+  else if (k == "lb_variant") *value = 100 * h->lb_pipe + 10 * (h->lb_tpc > 0 ? 1 : 0) + h->lb_minb;
+  else if (k == "in_place") *value = h->in_place ? 1 : 0;
+  else if (k == "p2p") *value = h->p2p ? 1 : 0;
+  else if (k == "ipc") *value = (h->peer_ipc[0] || h->peer_ipc[1]) ? 1 : 0;
+  else if (k == "nranks") *value = h->nranks;
+  else if (k == "rank") *value = h->rank;
+  else if (k == "fluid_nodes_with_halo") *value = h->nf;
+  else return fail(h, LBG_ERR_INVALID_ARG, "lbg_get_info: unknown key " + k);
   return LBG_OK;
 }
 

@@ -75,26 +75,103 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Tiles of BLOCK consecutive fids start on a 32-fid boundary whatever fid_begin is (a plane may start at
-// any fid): every warp then reads and writes whole, aligned 256-byte runs of each array.  Threads of
-// the first tile that fall before fid_begin skip (`ff < fid_begin`).
-#ifndef LBG_ALIGN_TILES
-#define LBG_ALIGN_TILES 1
-#endif
-__host__ __device__ __forceinline__ long long tile_base(long long fid_begin) {
-#if LBG_ALIGN_TILES
-  return fid_begin & ~31LL;
-#else
-  return fid_begin;
-#endif
-}
 __device__ __forceinline__ long long first_fid(long long fid_begin) {
   return tile_base(fid_begin) + (long long)blockIdx.x * BLOCK + threadIdx.x;
 }
 
-inline int clamp_grid(long long n, int grid) {
-  const long long b = (n + 31 + BLOCK - 1) / BLOCK;  // + 31: tiles start on the 32-fid boundary below fid_begin
-  return (int)(b < 1 ? 1 : (b < grid ? b : grid));
+// Tile schedule of a persistent CTA.  A tile is BLOCK consecutive fids starting on a 32-fid boundary
+// (tile_base); thread t of the CTA owns fid tile_base + tile*BLOCK + t.  Two modes (Geo::tpc):
+//   static  (tpc == 0): CTA b visits tiles b, b + gridDim.x, ...; its "chunk" is all of them (id = b).
+//   dynamic (tpc  > 0): chunks of tpc consecutive tiles are handed out by an atomic counter, one chunk
+//                       ahead, so that the counter's round trip hides behind the current chunk.
+// Measured (profiles/streams_r4a.txt, streams_r4c.txt): a 19 -> 19 fp64 stream moves 5.2-5.8 TB/s with the static
+// schedule and 6.4-6.8 TB/s with the dynamic one on the same persistent grid -- the SMs do not all get the same
+// share of HBM bandwidth, and a static partition runs at the pace of the slowest.
+// All threads of the CTA must call init / advance together (they contain __syncthreads in dynamic mode).
+struct Tiles {
+  int tile;    // current tile, -1 when the CTA has no more work
+  int chunk;   // id of the chunk the current tile belongs to (slot of a per-chunk partial result)
+  int k;       // tiles of the current chunk visited before this one
+  int cn;      // dynamic: the chunk after this one, already fetched
+  int ntiles, nchunks, tpc, par;
+  unsigned int* counter;
+  unsigned int* slot;  // two words of shared memory
+
+  __device__ __forceinline__ int grab() {
+    if (threadIdx.x == 0) slot[par] = atomicAdd(counter, 1u);
+    __syncthreads();
+    const unsigned int v = slot[par];
+    par ^= 1;
+    return v < (unsigned int)nchunks ? (int)v : nchunks;
+  }
+  __device__ __forceinline__ void init(const Geo& geo, long long fid_begin, long long fid_end, unsigned int* counter_,
+                                       unsigned int* slot_, int ntiles_override = -1) {
+    ntiles = ntiles_override >= 0 ? ntiles_override : (int)((fid_end - tile_base(fid_begin) + BLOCK - 1) / BLOCK);
+    tpc = geo.tpc;
+    counter = counter_;
+    slot = slot_;
+    par = 0;
+    k = 0;
+    if (tpc > 0) {
+      nchunks = (ntiles + tpc - 1) / tpc;
+      chunk = grab();
+      cn = chunk < nchunks ? grab() : nchunks;
+      tile = chunk < nchunks ? chunk * tpc : -1;
+    } else {
+      nchunks = (int)gridDim.x;
+      chunk = (int)blockIdx.x;
+      cn = nchunks;
+      tile = (int)blockIdx.x < ntiles ? (int)blockIdx.x : -1;
+    }
+  }
+  // the tile advance() will move to, -1 if none (lets the caller prefetch for it)
+  __device__ __forceinline__ int next_tile() const {
+    if (tpc > 0) {
+      if (k + 1 < tpc && tile + 1 < ntiles) return tile + 1;
+      return cn < nchunks ? cn * tpc : -1;
+    }
+    const int t = tile + (int)gridDim.x;
+    return t < ntiles ? t : -1;
+  }
+  // move to the next tile; true if the current tile was the last one of its chunk
+  __device__ __forceinline__ bool advance() {
+    if (tpc > 0) {
+      if (k + 1 < tpc && tile + 1 < ntiles) {
+        ++k;
+        ++tile;
+        return false;
+      }
+      chunk = cn;
+      k = 0;
+      if (chunk < nchunks) {
+        tile = chunk * tpc;
+        cn = grab();
+      } else {
+        tile = -1;
+      }
+      return true;
+    }
+    tile += (int)gridDim.x;
+    if (tile < ntiles) return false;
+    tile = -1;
+    return true;
+  }
+};
+
+// after its last tile every CTA checks in; the last one of the launch resets the counters for the next launch
+__device__ __forceinline__ bool cta_checks_in_last(Ctrl* ctrl) {
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(&ctrl->ticket, 1u);
+    s_last = (done == gridDim.x - 1) ? 1 : 0;
+    if (s_last) {
+      ctrl->tile_next = 0;
+      ctrl->ticket = 0;
+    }
+  }
+  __syncthreads();
+  return s_last != 0;
 }
 
 }  // namespace lbg

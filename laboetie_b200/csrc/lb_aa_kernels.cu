@@ -71,8 +71,14 @@ __global__ void __launch_bounds__(BLOCK, 2) aa_even_kernel(const __grid_constant
   if (s_stop) return;
   const long long nfa = a.geo.nfa;
   double* f = a.fout;  // in place: fin == fout
-  for (long long ff = first_fid(a.fid_begin); ff < a.fid_end; ff += (long long)gridDim.x * BLOCK) {
-    if (ff < a.fid_begin) continue;
+  __shared__ unsigned int s_slot[2];
+  Tiles ts;
+  ts.init(a.geo, a.fid_begin, a.fid_end, &a.ctrl->tile_next, s_slot);
+  const long long base = tile_base(a.fid_begin) + threadIdx.x;
+  while (ts.tile >= 0) {
+    const long long ff = base + (long long)ts.tile * BLOCK;
+    ts.advance();
+    if (ff < a.fid_begin || ff >= a.fid_end) continue;
     const int fid = (int)ff;
     double n[NV];
     static_for<0, NV>([&](auto Lc) {
@@ -97,6 +103,7 @@ __global__ void __launch_bounds__(BLOCK, 2) aa_even_kernel(const __grid_constant
       f[(long long)inv(L) * nfa + fid] = n[L];
     });
   }
+  if (a.geo.tpc > 0) cta_checks_in_last(a.ctrl);
 }
 
 // S(t) -> N(t+1)
@@ -109,13 +116,20 @@ __global__ void __launch_bounds__(BLOCK, 2) aa_odd_kernel(const __grid_constant_
   const Geo& geo = a.geo;
   const long long nfa = geo.nfa;
   double* f = a.fout;
-  const long long first = first_fid(a.fid_begin);
-  const long long stride = (long long)gridDim.x * BLOCK;
-  uint32_t gi_next = first < a.fid_end ? __ldg(geo.gidx + first) : 0u;
-  for (long long ff = first; ff < a.fid_end; ff += stride) {
+  __shared__ unsigned int s_slot[2];
+  Tiles ts;
+  ts.init(geo, a.fid_begin, a.fid_end, &a.ctrl->tile_next, s_slot);
+  const long long base = tile_base(a.fid_begin) + threadIdx.x;
+  long long ff_next = ts.tile >= 0 ? base + (long long)ts.tile * BLOCK : -1;
+  uint32_t gi_next = (ff_next >= 0 && ff_next < a.fid_end) ? __ldg(geo.gidx + ff_next) : 0u;
+  while (ts.tile >= 0) {
+    const long long ff = ff_next;
     const uint32_t gi = gi_next;
-    if (ff + stride < a.fid_end) gi_next = __ldg(geo.gidx + ff + stride);
-    if (ff < a.fid_begin) continue;
+    const int tn = ts.next_tile();
+    ff_next = tn >= 0 ? base + (long long)tn * BLOCK : -1;
+    if (ff_next >= 0 && ff_next < a.fid_end) gi_next = __ldg(geo.gidx + ff_next);
+    ts.advance();
+    if (ff < a.fid_begin || ff >= a.fid_end) continue;
     const int fid = (int)ff;
     const int g = (int)(gi & GIDX_MASK);
     const Nb nb = neighbours(geo, g);
@@ -154,6 +168,7 @@ __global__ void __launch_bounds__(BLOCK, 2) aa_odd_kernel(const __grid_constant_
       f[(long long)arr * nfa + idx] = n[L];
     });
   }
+  if (geo.tpc > 0) cta_checks_in_last(a.ctrl);
 }
 
 // Reference state of the current step from either layout: n(t)(r,·), then density, momentum, the

@@ -103,15 +103,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_const
   const long long nfa = geo.nfa;
   double dmax = 0.0;
   bool any_neg = false;
-  // tiles of BLOCK consecutive fluid nodes; the dense index of the next tile's node is fetched one
-  // iteration ahead so that its DRAM latency does not sit in front of the dependent population loads
-  const long long first = first_fid(a.fid_begin);
-  const long long stride = (long long)gridDim.x * BLOCK;
-  uint32_t gi_next = first < a.fid_end ? __ldg(geo.gidx + first) : 0u;
-  for (long long ff = first; ff < a.fid_end; ff += stride) {
+  // tiles of BLOCK consecutive fluid nodes (schedule: lattice.cuh Tiles); the dense index of the next tile's
+  // node is fetched one iteration ahead so that its DRAM latency does not sit in front of the dependent
+  // population loads
+  __shared__ unsigned int s_slot[2];
+  Tiles ts;
+  ts.init(geo, a.fid_begin, a.fid_end, &a.ctrl->tile_next, s_slot);
+  const long long base = tile_base(a.fid_begin) + threadIdx.x;
+  long long ff_next = ts.tile >= 0 ? base + (long long)ts.tile * BLOCK : -1;
+  uint32_t gi_next = (ff_next >= 0 && ff_next < a.fid_end) ? __ldg(geo.gidx + ff_next) : 0u;
+  while (ts.tile >= 0) {
+    const long long ff = ff_next;
     const uint32_t gi = gi_next;
-    if (ff + stride < a.fid_end) gi_next = __ldg(geo.gidx + ff + stride);
-    if (ff < a.fid_begin) continue;
+    const int tn = ts.next_tile();
+    ff_next = tn >= 0 ? base + (long long)tn * BLOCK : -1;
+    if (ff_next >= 0 && ff_next < a.fid_end) gi_next = __ldg(geo.gidx + ff_next);
+    ts.advance();
+    if (ff < a.fid_begin || ff >= a.fid_end) continue;
     const int fid = (int)ff;
     const int g = (int)(gi & GIDX_MASK);
     const Nb nb = neighbours(geo, g);
@@ -156,6 +164,136 @@ __global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_const
 #pragma unroll
       for (int w = 1; w < BLOCK / 32; ++w) v = fmax(v, s_red[w]);
       // non-negative doubles order like their bit patterns
+      atomicMax(&a.l2_slots[2 * a.batch_idx], (unsigned long long)__double_as_longlong(v));
+    }
+    if (s_neg) atomicMax(&a.l2_slots[2 * a.batch_idx + 1], 1ull);
+  }
+  if (geo.tpc > 0) cta_checks_in_last(a.ctrl);
+}
+
+// ---------------------------------------------------------------------------
+// Two-stage software pipeline of the step kernel.  The plain kernel above serialises, per warp and tile,
+// [18 rank lookups (an L2 round trip)] -> [19 population loads (a DRAM round trip; two when the register
+// allocator interleaves late lookups with the first loads, which then share a scoreboard)] -> arithmetic ->
+// stores; ncu's source view puts 35 % of its stall samples on the lookup words and 22 % on the populations
+// (profiles/r4f_lb_source_stalls.txt).  Here the lookups of tile i+1 are resolved while the population loads
+// of tile i are in flight, and handed to the next iteration through 18 packed words per thread in shared
+// memory (source fid | source-is-fluid << 31; each thread reads only its own column: no barrier).  An
+// iteration then starts with 18 LDS and issues all 22 loads of its tile back to back: one exposed round trip.
+// The dense index (gidx) is fetched two tiles ahead.  Static tile-stride schedule.
+constexpr uint32_t SRC_FLUID = 0x80000000u;
+
+template <bool TAU1, int FMODE, bool CHECK, bool WRITEJ, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) lb_step_pipe_kernel(const __grid_constant__ LBArgs a) {
+  __shared__ uint32_t s_src[NV - 1][BLOCK];
+  __shared__ int s_stop;
+  __shared__ double s_red[BLOCK / 32];
+  __shared__ int s_neg;
+  if (threadIdx.x == 0) {
+    int stop = *(volatile int*)&a.ctrl->stop;
+    if (!stop && a.batch_idx > 0 && *(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 1) + 1] != 0ull) {
+      a.ctrl->stop = 1;  // equilibration.f90:248
+      stop = 1;
+    }
+    if (!stop && a.prev_checked && a.prev_may_stop) {
+      const double prev =
+          __longlong_as_double((long long)*(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 1)]);
+      if (prev <= a.target) {  // equilibration.f90:346
+        a.ctrl->stop = 1;
+        a.ctrl->stop_idx = a.batch_idx;
+        stop = 1;
+      }
+    }
+    s_stop = stop;
+    s_neg = 0;
+  }
+  __syncthreads();
+  if (s_stop) return;
+
+  const Geo& geo = a.geo;
+  const long long nfa = geo.nfa;
+  double dmax = 0.0;
+  bool any_neg = false;
+  const long long stride = (long long)gridDim.x * BLOCK;
+  const long long first = first_fid(a.fid_begin);
+  auto valid = [&](long long ff) { return ff >= a.fid_begin && ff < a.fid_end; };
+  // resolve the 18 pull sources of node (fid, g) and park them in this thread's column of s_src
+  auto resolve = [&](int fid, int g) {
+    const Nb nb = neighbours(geo, g);
+    static_for<1, NV>([&](auto Lc) {
+      constexpr int L = decltype(Lc)::value;
+      int fsrc;
+      const bool src_fluid = lookup(geo, g + offset_plus<inv(L)>(nb), fsrc);
+      s_src[L - 1][threadIdx.x] = src_fluid ? ((uint32_t)fsrc | SRC_FLUID) : (uint32_t)fid;
+    });
+  };
+  // prologue: sources of the first tile, dense index of the second
+  if (valid(first)) resolve((int)first, (int)(__ldg(geo.gidx + first) & GIDX_MASK));
+  uint32_t gi1 = valid(first + stride) ? __ldg(geo.gidx + first + stride) : 0u;  // tile i+1
+  for (long long ff = first; ff < a.fid_end; ff += stride) {
+    const bool ok = valid(ff);
+    const int fid = (int)ff;
+    double n[NV];
+    double ox = 0, oy = 0, oz = 0;
+    if (ok) {
+      uint32_t src[NV - 1];
+      static_for<1, NV>([&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        src[L - 1] = s_src[L - 1][threadIdx.x];
+      });
+      n[0] = ld_pop(a.fin + fid);
+      static_for<1, NV>([&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        const uint32_t e = src[L - 1];
+        const int arr = (e & SRC_FLUID) ? L : inv(L);
+        n[L] = ld_pop(a.fin + (long long)arr * nfa + (long long)(e & ~SRC_FLUID));
+      });
+      if constexpr (CHECK) {
+        ox = a.jold[fid];
+        oy = a.jold[nfa + fid];
+        oz = a.jold[2 * nfa + fid];
+      }
+    }
+    // while those loads are in flight: dense index of tile i+2, pull sources of tile i+1
+    const uint32_t gi = gi1;
+    if (valid(ff + 2 * stride)) gi1 = __ldg(geo.gidx + ff + 2 * stride);
+    if (valid(ff + stride)) resolve((int)(ff + stride), (int)(gi & GIDX_MASK));
+    if (!ok) continue;
+    double fjx = 0, fjy = 0, fjz = 0, fcx = 0, fcy = 0, fcz = 0;
+    if constexpr (FMODE == FORCE_UNIFORM) {
+      fjx = a.fj[0]; fjy = a.fj[1]; fjz = a.fj[2];
+      fcx = a.fc[0]; fcy = a.fc[1]; fcz = a.fc[2];
+    } else if constexpr (FMODE == FORCE_FIELD) {
+      fjx = a.fj_field[fid]; fjy = a.fj_field[nfa + fid]; fjz = a.fj_field[2 * nfa + fid];
+      fcx = a.fc_field[fid]; fcy = a.fc_field[nfa + fid]; fcz = a.fc_field[2 * nfa + fid];
+    }
+    double rho, jx, jy, jz;
+    bool neg;
+    moments(n, fjx / 2.0, fjy / 2.0, fjz / 2.0, rho, jx, jy, jz, neg);
+    any_neg |= neg;
+    if constexpr (CHECK) dmax = fmax(dmax, fmax(fabs(jx - ox), fmax(fabs(jy - oy), fabs(jz - oz))));
+    if constexpr (WRITEJ) {
+      a.jnew[fid] = jx;
+      a.jnew[nfa + fid] = jy;
+      a.jnew[2 * nfa + fid] = jz;
+    }
+    collide<TAU1, FMODE != FORCE_NONE>(n, a.k, rho, jx, jy, jz, fcx, fcy, fcz, a.w1, a.w2, a.w3);
+    static_for<0, NV>([&](auto Lc) {
+      constexpr int L = decltype(Lc)::value;
+      a.fout[(long long)L * nfa + fid] = n[L];
+    });
+  }
+  if (any_neg) s_neg = 1;
+  if constexpr (CHECK) {
+    dmax = warp_max(dmax);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = dmax;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if constexpr (CHECK) {
+      double v = s_red[0];
+#pragma unroll
+      for (int w = 1; w < BLOCK / 32; ++w) v = fmax(v, s_red[w]);
       atomicMax(&a.l2_slots[2 * a.batch_idx], (unsigned long long)__double_as_longlong(v));
     }
     if (s_neg) atomicMax(&a.l2_slots[2 * a.batch_idx + 1], 1ull);
@@ -292,6 +430,12 @@ inline int small_grid(long long n) {
 
 template <bool TAU1, int FMODE, int MINB>
 void launch_step_cw(const LBArgs& a, bool check, bool writej, int grid, cudaStream_t st) {
+  if (a.pipe) {
+    if (check) lb_step_pipe_kernel<TAU1, FMODE, true, true, MINB><<<grid, BLOCK, 0, st>>>(a);
+    else if (writej) lb_step_pipe_kernel<TAU1, FMODE, false, true, MINB><<<grid, BLOCK, 0, st>>>(a);
+    else lb_step_pipe_kernel<TAU1, FMODE, false, false, MINB><<<grid, BLOCK, 0, st>>>(a);
+    return;
+  }
   if (check) lb_step_kernel<TAU1, FMODE, true, true, MINB><<<grid, BLOCK, 0, st>>>(a);
   else if (writej) lb_step_kernel<TAU1, FMODE, false, true, MINB><<<grid, BLOCK, 0, st>>>(a);
   else lb_step_kernel<TAU1, FMODE, false, false, MINB><<<grid, BLOCK, 0, st>>>(a);
@@ -364,9 +508,9 @@ int launch_moments(const MomArgs& a, int fmode, int grid, cudaStream_t st) {
 int occupancy_grid_lb(int sm_count, int minb) {
   int per_sm = 0;
   if (minb >= 3)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lb_step_kernel<true, FORCE_UNIFORM, true, true, 3>, BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lb_step_pipe_kernel<true, FORCE_UNIFORM, true, true, 3>, BLOCK, 0);
   else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lb_step_kernel<true, FORCE_UNIFORM, true, true, 2>, BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lb_step_pipe_kernel<true, FORCE_UNIFORM, true, true, 2>, BLOCK, 0);
   if (per_sm < 1) per_sm = 1;
   return sm_count * per_sm;
 }

@@ -39,6 +39,10 @@ struct Geo {
   uint32_t mul_plane, mul_lx;
   int sh_plane, sh_lx;
   int zero;               // always 0, unknown to the compiler: lets a kernel make one value depend on others (issue order)
+  // Tile schedule of the step kernels (lattice.cuh Tiles): a persistent grid either way; tpc > 0: an atomic
+  // counter hands out chunks of tpc consecutive tiles of BLOCK fids (SMs that get more HBM bandwidth take more
+  // chunks); tpc == 0: static tile-stride loop.
+  int tpc;
 };
 
 // Round-up multiplier for an exact unsigned division of 31-bit dividends (Granlund & Montgomery):
@@ -64,7 +68,8 @@ struct Ctrl {
   int stop;                 // set by the first kernel that sees the criterion met
   int neg_step_idx;         // 1 + batch index of the first step with a negative population (0 = none)
   int stop_idx;             // 1 + batch index of the converged step
-  unsigned int ticket;      // last-block election for the vacf reduction
+  unsigned int ticket;      // CTAs that have finished: elects the last one (vacf reduction, counter reset)
+  unsigned int tile_next;   // dynamic tile schedule: next chunk to hand out (reset by the last CTA of a launch)
 };
 
 enum ForceMode { FORCE_NONE = 0, FORCE_UNIFORM = 1, FORCE_FIELD = 2 };
@@ -88,6 +93,7 @@ struct LBArgs {
   int prev_may_stop;             // ... and its global t-1 > 2
   double target;
   Ctrl* ctrl;
+  int pipe;                      // two-stage software pipeline (lb_step_pipe_kernel) instead of the plain kernel
 };
 
 struct CollideArgs {
@@ -183,6 +189,26 @@ struct ProfileArgs {
   double eps;
   double* out;  // 5 per row: sum jx, jy, jz, sum rho, count(rho > eps)
 };
+
+// Tiles of BLOCK consecutive fids start on a 32-fid boundary whatever fid_begin is (a plane may start at
+// any fid): every warp then reads and writes whole, aligned 256-byte runs of each array.  Threads of
+// the first tile that fall before fid_begin skip (`ff < fid_begin`).
+#ifndef LBG_ALIGN_TILES
+#define LBG_ALIGN_TILES 1
+#endif
+__host__ __device__ __forceinline__ long long tile_base(long long fid_begin) {
+#if LBG_ALIGN_TILES
+  return fid_begin & ~31LL;
+#else
+  return fid_begin;
+#endif
+}
+
+inline int clamp_grid(long long n, int grid) {
+  const long long b = (n + 31 + BLOCK - 1) / BLOCK;  // + 31: tiles start on the 32-fid boundary below fid_begin
+  return (int)(b < 1 ? 1 : (b < grid ? b : grid));
+}
+
 
 // launchers (geometry.cu / lb_kernels.cu / mp_kernels.cu).  Each returns the number of kernels launched.
 int launch_build_bits(int plane, int nzl, const int8_t* nature_halo, uint2* words, long long nwords, cudaStream_t st);

@@ -657,3 +657,79 @@ def test_device_side_geometry_builders(label, shape):
         with lb.LaboetieGPU(label=label, shape=shape, k0=k0, nzl=nzl) as slab:
             assert np.array_equal(slab.nature(), nat[k0:k0 + nzl])
             assert np.array_equal(slab.interfacial(), O.detect_interfacial(nat)[k0:k0 + nzl])
+
+
+# --------------------------------------------------------------------------- BASELINE-shaped lattices
+def _bench_geoms():
+    from laboetie_b200 import synthetic as S
+    return [
+        # (id, builder, force, neighbour table expected by the library's own heuristic)
+        ("porous128x96x24", lambda: S.porous_spheres(128, 96, 24, radius=6), [1e-6, 0.0, 0.0], 1),   # BASELINE config 5
+        ("bcc64", lambda: S.bcc(64, 64, 64), [1e-6, 0.0, 0.0], 1),                                   # config 3
+        ("cylinder65x65x16", lambda: S.cylinder(65, 65, 16), [0.0, 0.0, 1e-6], 1),                   # config 4
+        ("bernoulli96x64x16", lambda: S.bernoulli(96, 64, 16), [1e-6, 0.0, 0.0], 1),                 # cfg5b
+        ("slit64x64x24", lambda: S.slit(64, 64, 24), [1e-6, 0.0, 0.0], 1),                           # config 2 (phi < 0.95)
+    ]
+
+
+BENCH_GEOMS = _bench_geoms()
+
+
+@pytest.mark.parametrize("in_place", [False, True], ids=["two-lattice", "in-place"])
+@pytest.mark.parametrize("name,mk,f,want_nbt", BENCH_GEOMS, ids=[g[0] for g in BENCH_GEOMS])
+def test_benchmark_shaped_lattices_against_oracle(name, mk, f, want_nbt, in_place, monkeypatch):
+    """The geometries bench.py measures (overlapping-sphere porous medium, BCC, cylinder, Bernoulli noise, slit),
+    at sizes the oracle runs in seconds, on the code paths the LIBRARY picks by itself (no LBG_MP_NBT / LBG_LB_*
+    overrides: the default neighbour-table heuristic, with periodic-x-seam nodes present): 12 LB steps with the
+    per-step check across the force switch, then 12 propagate steps with adsorption, everything per node
+    bit for bit, l2err history bit for bit, vacf to summation order."""
+    lb = _gpu()
+    for v in ("LBG_MP_NBT", "LBG_LB_MINB", "LBG_LB_PIPE", "LBG_LB_TPC", "LBG_MP_TPC", "LBG_MP_STRIP_ROWS"):
+        monkeypatch.delenv(v, raising=False)
+    nat = mk()
+    itf = O.detect_interfacial(nat)
+    tau, Db, ka, kd = 0.9, 0.01, 0.1, 0.01
+    st = O.LBState(nat, 1.0, tau)
+    ref_h = [st.step()[1] for _ in range(4)]
+    st.set_force_uniform(f)
+    ref_h += [st.step()[1] for _ in range(8)]
+    mp = O.MPState(nat, itf, st.rho, st.jx, st.jy, st.jz, f, Db, ka, kd)
+    ref_v = np.array([mp.propagate()[1] for _ in range(12)])
+    with lb.LaboetieGPU(nat) as sim:
+        if in_place:
+            sim.lb_set_in_place(True)
+        assert np.array_equal(sim.interfacial(), itf)
+        sim.lb_init(1.0)
+        d1, _, h1 = sim.lb_step(4, tau=tau, check_every=1, target_error=-1.0)
+        sim.lb_set_force_uniform(f)
+        d2, _, h2 = sim.lb_step(8, tau=tau, check_every=1, target_error=-1.0)
+        assert d1 == 4 and d2 == 8
+        assert np.array_equal(np.concatenate([h1, h2]), np.array(ref_h))
+        rho, jx, jy, jz = sim.lb_moments()
+        assert np.array_equal(rho, st.rho) and np.array_equal(jx, st.jx)
+        assert np.array_equal(jy, st.jy) and np.array_equal(jz, st.jz)
+        assert np.array_equal(sim.lb_populations(), st.n)
+        v0 = sim.mp_init(Db, ka, kd, f)
+        assert sim.info("mp_neighbour_table") == want_nbt
+        tol = sum_rtol(18 * nat.size)
+        assert rel_err(v0, mp.vacf0) <= tol
+        done, conv, v = sim.mp_step(12)
+        assert done == 12 and not conv
+        P, A = sim.mp_download()
+        assert np.array_equal(P, mp.P[0])
+        assert np.array_equal(A, mp.Pads[0])
+        assert (np.abs(v - ref_v) <= tol * np.abs(mp.vacf0).max()).all()
+
+
+def test_shape_checks_in_the_python_binding():
+    lb = _gpu()
+    nat = random_nature(6, 5, 4, 0.2, 3)
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_init(1.0)
+        bad = np.zeros((5, 5, 6))
+        with pytest.raises(lb.LbgError):
+            sim.lb_set_force_field(bad, bad, bad)
+        with pytest.raises(lb.LbgError):
+            sim.lb_upload(np.zeros((19,) + bad.shape), bad, bad, bad, bad)
+        with pytest.raises(lb.LbgError):
+            sim.info("no-such-key")
