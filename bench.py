@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--cpu-lattice", default="auto", choices=["auto", "full", "crop"],
+                    help="--impl reference: the workload's whole single-GPU lattice (needs ~60 GB of host memory for cfg5w) or a crop")
+    ap.add_argument("--no-verify", action="store_true", help="skip the parity check of the launched configuration")
     ap.add_argument("--in-place", action="store_true", help="Phase A with the AA pattern (one population buffer)")
     ap.add_argument("--also", default="cfg2,cfg3", help="extra single-GPU workloads reported under 'also' (N=1 only)")
     return ap.parse_args()
@@ -133,14 +136,28 @@ def algorithmic_bytes(nf, nif, n, check):
 
 
 # --------------------------------------------------------------------------- CPU arm
-def cpu_run(workload, seconds, steps=None, threads=None):
-    """The reference-shaped OpenMP restatement (oracle/) on a bounded crop of the same workload."""
+def host_mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 2 ** 20
+    except OSError:
+        pass
+    return 0.0
+
+
+def cpu_run(workload, seconds, steps=None, threads=None, full=False):
+    """The reference-shaped OpenMP restatement (oracle/) on the workload's own lattice (full=True) or on a
+    bounded crop of it."""
     from oracle import oracle as O
     from laboetie_b200 import synthetic as S
     builder, lx, ly, lz_per, f_ext, desc = S.WORKLOADS[workload]
-    cx, cy, cz = min(lx, 256), min(ly, 256), min(lz_per, 32)
-    full_kw = {}
-    nat = builder(lx, ly, lz_per, k0=0, nz=cz)[:, :cy, :cx].copy() if workload != "cfg3" else builder(64, 64, 64)[:32]
+    if full:
+        cx, cy, cz = lx, ly, lz_per
+        nat = builder(lx, ly, lz_per)
+    else:
+        cx, cy, cz = min(lx, 256), min(ly, 256), min(lz_per, 32)
+        nat = builder(lx, ly, lz_per, k0=0, nz=cz)[:, :cy, :cx].copy() if workload != "cfg3" else builder(64, 64, 64)[:32]
     nat = np.ascontiguousarray(nat)
     if nat.all():
         nat.flat[0] = 0
@@ -154,7 +171,8 @@ def cpu_run(workload, seconds, steps=None, threads=None):
     st = O.LBState(nat, 1.0, TAU)
     st.set_force_uniform(f_ext)
     n = nat.size
-    st.step()  # warm-up (page faults)
+    if not full:
+        st.step()  # warm-up (page faults); at full size one step is ~40 s and the run is kept to a single one
     t0 = time.perf_counter()
     k = 0
     while True:
@@ -163,36 +181,124 @@ def cpu_run(workload, seconds, steps=None, threads=None):
         if (steps and k >= steps) or (not steps and time.perf_counter() - t0 > seconds / 2):
             break
     t_lb = (time.perf_counter() - t0) / k
-    mp = O.MPState(nat, itf, st.rho, st.jx, st.jy, st.jz, f_ext, TRACER["Db"], TRACER["ka"], TRACER["kd"])
-    mp.propagate()
+    rho, jx, jy, jz = st.rho, st.jx, st.jy, st.jz
+    del st          # the reference frees its populations before Phase B too (drop_tracers.f90:85)
+    mp = O.MPState(nat, itf, rho, jx, jy, jz, f_ext, TRACER["Db"], TRACER["ka"], TRACER["kd"])
+    if not full:
+        mp.propagate()
     t0 = time.perf_counter()
     for _ in range(k):
         mp.propagate()
     t_mp = (time.perf_counter() - t0) / k
     mlups = n / (t_lb + t_mp) / 1e6
     return dict(value=mlups, unit="MLUPS", cores=threads or ncores, kind="port",
-                sample=f"{cx}x{cy}x{nat.shape[0]} crop of {workload}, {k} LB + {k} MP steps, "
+                sample=f"{cx}x{cy}x{nat.shape[0]} {'(the whole lattice)' if full else 'crop'} of {workload}, {k} LB + {k} MP steps, "
                        f"oracle/ C++/OpenMP restatement (no Fortran compiler: reference binary unavailable)",
-                lb_mlups=n / t_lb / 1e6, mp_mlups=n / t_mp / 1e6, steps=k), (t_lb + t_mp) * 1e3
+                lb_mlups=n / t_lb / 1e6, mp_mlups=n / t_mp / 1e6, steps=k, lattice=[cx, cy, int(nat.shape[0])],
+                full=bool(full)), (t_lb + t_mp) * 1e3
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    warm = max(args.warmup, 0)
-    res, ms = cpu_run(args.workload, args.cpu_seconds, steps=max(1, min(args.steps, 4)))
-    # the reference's README recommends 4 OpenMP threads (README.md:94): reported beside the all-cores figure
-    res4, _ = cpu_run(args.workload, args.cpu_seconds, steps=max(1, min(args.steps, 2)), threads=4)
+    from laboetie_b200 import synthetic as S
+    builder, lx, ly, lz_per, f_ext, desc = S.WORKLOADS[args.workload]
+    # The product arm's own lattice (one GPU's share of the weak-scaling workload) when the host can hold the
+    # reference's arrays for it (~0.45 KB per node at peak: populations, per-thread streaming copies, moments),
+    # else a crop.  One step of the full cfg5w lattice is ~40 s on 16 cores, so a single LB + MP step is timed
+    # there, without a warm-up step, and `steps` / `warmup` say so.
+    need_gb = 450.0 * lx * ly * lz_per / 2 ** 30
+    full = (args.cpu_lattice == "full") or (args.cpu_lattice == "auto" and host_mem_available_gb() > need_gb + 8)
+    if full:
+        res, ms = cpu_run(args.workload, args.cpu_seconds, steps=1, full=True)
+        warm = 0
+    else:
+        res, ms = cpu_run(args.workload, args.cpu_seconds, steps=max(1, min(args.steps, 4)))
+        warm = 1
+    # the reference's README recommends 4 OpenMP threads (README.md:94): reported beside the all-cores figure (crop)
+    res4, _ = cpu_run(args.workload, args.cpu_seconds, steps=1, threads=4)
     line = {"metric": "MLUPS (fp64 D3Q19 collide-stream + moment propagation)", "value": res["value"], "unit": "MLUPS",
-            "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "timed_steps": res["steps"], "warmup": warm,
-            "ms_per_step": ms, "cpu_4_threads": {"value": res4["value"], "unit": "MLUPS", "cores": res4["cores"]},
+            "impl": "reference", "n_gpus": args.gpus, "steps": res["steps"], "requested_steps": args.steps, "warmup": warm,
+            "ms_per_step": ms,
+            "cpu_4_threads": {"value": res4["value"], "unit": "MLUPS", "cores": res4["cores"], "sample": res4["sample"]},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "tau": TAU, **TRACER},
+            "config": {"workload": args.workload, "description": desc, "lattice": res["lattice"],
+                       "whole_lattice_of_the_gpu_arm_at_n1": res["full"], "tau": TAU, **TRACER, "check_every": 1},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "lb_mlups": res["lb_mlups"], "mp_mlups": res["mp_mlups"]}
     print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- parity of the launched configuration
+def kernel_source_hash():
+    """sha1 over the kernel sources: ncu-derived traffic figures are only valid for the code they were taken on."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "laboetie_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def verify_launch(dist, rank, nranks, local):
+    """Run a small porous lattice through exactly the path this launch uses -- one process per GPU, z-slabs, halos
+    pushed through CUDA-IPC-mapped peer memory, scalar all-reduces through the peers' mailboxes -- and compare
+    every per-node result with the CPU oracle on rank 0, bit for bit (the oracle is the checker here, nothing of
+    it is timed).  12 LB steps with the per-step check across the force switch, 8 propagate steps with adsorption."""
+    import laboetie_b200 as lb
+    from laboetie_b200 import api, synthetic as S
+    lx, ly, lz = 96, 40, 6 * nranks
+    f_ext, tau = [1e-5, 0.0, 2e-5], 0.9
+    k0, nzl = api.partition(lz, nranks, rank)
+    if nranks == 1:
+        sim = lb.LaboetieGPU(S.porous_spheres(lx, ly, lz, radius=5), device=local)
+    else:
+        sim = lb.LaboetieGPU(S.porous_spheres(lx, ly, lz, radius=5, k0=k0 - 1, nz=nzl + 2), device=local, lz_global=lz,
+                             k0=k0, slab=True)
+        uid = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        sim.comm_init(nranks, rank, uid[0])
+    path = "single GPU" if nranks == 1 else ("ipc" if sim.info("ipc") else ("peer" if sim.info("p2p") else "nccl"))
+    sim.lb_init(1.0)
+    _, _, h1 = sim.lb_step(4, tau=tau, check_every=1, target_error=-1.0)
+    sim.lb_set_force_uniform(f_ext)
+    _, _, h2 = sim.lb_step(8, tau=tau, check_every=1, target_error=-1.0)
+    mine = dict(k0=k0, nzl=nzl, hist=np.concatenate([h1, h2]), n=sim.lb_populations(), mom=sim.lb_moments())
+    mine["v0"] = sim.mp_init(TRACER["Db"], TRACER["ka"], TRACER["kd"], f_ext)
+    done, _, mine["v"] = sim.mp_step(8)
+    mine["P"], mine["A"] = sim.mp_download()
+    sim.close()
+    parts = [mine]
+    if dist is not None:
+        parts = [None] * nranks if rank == 0 else None
+        dist.gather_object(mine, parts, dst=0)
+    if rank != 0:
+        return None
+    from oracle import oracle as O
+    nat = S.porous_spheres(lx, ly, lz, radius=5)
+    st = O.LBState(nat, 1.0, tau)
+    ref_h = [st.step()[1] for _ in range(4)]
+    st.set_force_uniform(f_ext)
+    ref_h += [st.step()[1] for _ in range(8)]
+    mp = O.MPState(nat, O.detect_interfacial(nat), st.rho, st.jx, st.jy, st.jz, f_ext, TRACER["Db"], TRACER["ka"], TRACER["kd"])
+    ref_v = np.array([mp.propagate()[1] for _ in range(8)])
+    worst, ok = 0.0, True
+    for p in parts:
+        sl = slice(p["k0"], p["k0"] + p["nzl"])
+        pairs = [(p["n"], st.n[:, sl]), (p["P"], mp.P[0][sl]), (p["A"], mp.Pads[0][sl]), (p["hist"], np.array(ref_h))]
+        pairs += [(a, b[sl]) for a, b in zip(p["mom"], (st.rho, st.jx, st.jy, st.jz))]
+        for a, b in pairs:
+            ok = ok and np.array_equal(a, b)
+            worst = max(worst, float(np.abs(a - b).max()))
+        scale = np.abs(mp.vacf0).max()      # cross-node sums: to summation order (north_star: 1e-12 relative)
+        sum_err = max(float(np.abs(p["v"] - ref_v).max()), float(np.abs(p["v0"] - mp.vacf0).max())) / scale
+        ok = ok and sum_err <= 1e-12
+    return {"ok": bool(ok), "max_abs_diff": worst, "vacf_rel_diff": sum_err, "path": path, "lattice": [lx, ly, lz],
+            "ranks": nranks, "against": "CPU oracle on rank 0 (bit for bit per node; vacf to 1e-12 relative)",
+            "compared": "populations, density, momentum, l2err history (12 LB steps), P, Pads, vacf (8 MP steps)"}
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -246,6 +352,20 @@ def run_ours(args):
         sim.comm_init(nranks, rank, uid[0])
         return sim
 
+    # ---- parity of this very launch (process per GPU, IPC halos) against the oracle --------------
+    verify = None
+    if not args.no_verify:
+        try:
+            verify = verify_launch(dist, rank, nranks, local)
+        except Exception as e:  # noqa: BLE001  -- a failed check must show up in the line, not kill the measurement
+            verify = {"ok": False, "error": f"{type(e).__name__}: {e}"}
+
+    def must_run(res, k, what):
+        """The timed calls must execute exactly k steps (a convergence stop would inflate the rate silently)."""
+        done = res[0]
+        if done != k or res[1]:
+            raise RuntimeError(f"{what}: {done} of {k} steps executed (converged={res[1]}); the timing would be invalid")
+
     # ---- device-resident measurement --------------------------------------------------------
     sim = make_sim()
     nf, nif = sim.counts()
@@ -260,7 +380,7 @@ def run_ours(args):
     barrier()
     sim.sync()
     sim.timer_start()
-    sim.lb_step(K, tau=TAU, check_every=ce, target_error=-1.0, want_history=False)
+    must_run(sim.lb_step(K, tau=TAU, check_every=ce, target_error=-1.0, want_history=False), K, "timed LB steps")
     t_lb = sim.timer_stop()
     barrier()
     l_lb = sim.launches - l0
@@ -270,7 +390,7 @@ def run_ours(args):
     barrier()
     sim.sync()
     sim.timer_start()
-    sim.mp_step(K, want_history=False)
+    must_run(sim.mp_step(K, want_history=False), K, "timed MP steps")
     t_mp = sim.timer_stop()
     barrier()
     l_mp = sim.launches - l0
@@ -298,7 +418,8 @@ def run_ours(args):
         sim.sync()
         mark("lb_init")
         t_setup = time.perf_counter() - t0
-        done, conv, hist = sim.lb_step(K, tau=TAU, check_every=1, target_error=-1.0)
+        res = sim.lb_step(K, tau=TAU, check_every=1, target_error=-1.0)
+        must_run(res, K, "e2e LB steps")
         mark("lb_steps")          # K steps, l2err history D2H
         if bufs is not None:
             sim._ck(sim._L.lbg_lb_download_moments(sim._h, *bufs))
@@ -307,7 +428,8 @@ def run_ours(args):
         mark("moments_d2h")       # density and momentum density into pinned host arrays
         v0 = sim.mp_init(TRACER["Db"], TRACER["ka"], TRACER["kd"], f_ext)
         mark("mp_init")
-        done, conv, vac = sim.mp_step(K)
+        res = sim.mp_step(K)
+        must_run(res, K, "e2e MP steps")
         sim.sync()
         mark("mp_steps")          # K steps, vacf rows D2H
         t_e2e = allmax(time.perf_counter() - t0)
@@ -318,7 +440,9 @@ def run_ours(args):
                "h2d_bytes_per_step": float(nat.nbytes * nranks) / K,
                "d2h_bytes_per_step": float((4 * 8 * own) * nranks) / K + 8 + 24,
                "seconds": t_e2e, "setup_seconds": t_setup, "phase_seconds": phases,
-               "what": "create(H2D geometry)+lb_init+K LB steps(l2err history D2H)+moments D2H(pinned)+mp_init+K MP steps(vacf D2H); fixed costs (setup_seconds, the moments read-back, mp_init) amortised over K"}
+               "what": "create(H2D geometry)+lb_init+K LB steps(l2err history D2H)+moments D2H(pinned)+mp_init+K MP steps(vacf D2H); "
+                       "fixed costs (setup_seconds, the moments read-back, mp_init) amortised over K; the CUDA context and, "
+                       "at N>1, the NCCL bootstrap communicator exist already (one per process, reused across handles)"}
 
     # ---- the other BASELINE configurations that fit one GPU, device-resident numbers only (N=1) ------
     also = {}
@@ -376,6 +500,8 @@ def run_ours(args):
                                          "source": "profiles/streams_r3i.txt"}},
         "gpu_launches": int(l_lb + l_mp), "clocks": clocks,
     }
+    if verify is not None:
+        line["verify"] = verify
     if also:
         line["also"] = also
     if e2e:
@@ -383,13 +509,17 @@ def run_ours(args):
     if not args.no_cpu_baseline:
         res, _ = cpu_run(args.workload, args.cpu_seconds)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    # optional ncu-derived DRAM traffic for the dominant kernel (profiles/traffic_<workload>.json)
+    # ncu-derived DRAM traffic per launch of the two step kernels (profiles/traffic_<workload>.json, written by
+    # tools/ncu_traffic.py from one `ncu --set full` capture): reported only for N=1 and only if the file was
+    # taken on exactly these kernel sources -- otherwise null (a stale figure would be worse than none)
     tp = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
-    if os.path.exists(tp):
+    if nranks == 1 and os.path.exists(tp):
         try:
             tr = json.load(open(tp))
-            line["roofline"]["traffic"] = tr.get("lb_step_kernel_bytes_per_launch")
-            line["roofline"]["mp_step_kernel"]["traffic"] = tr.get("mp_step_kernel_bytes_per_launch")
+            if tr.get("kernel_source_hash") == kernel_source_hash():
+                line["roofline"]["traffic"] = tr.get("lb_step_kernel_bytes_per_launch")
+                line["roofline"]["mp_step_kernel"]["traffic"] = tr.get("mp_step_kernel_bytes_per_launch")
+                line["roofline"]["traffic_source"] = tr.get("source")
         except Exception:
             pass
     print(json.dumps(line))

@@ -17,6 +17,7 @@
 // ncclAllReduce.  NCCL is loaded with dlopen only when lbg_comm_init is called.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <climits>
@@ -25,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -36,8 +38,33 @@ using namespace lbg;
 namespace {
 
 constexpr int SLOT_CAP = 4096;  // steps per batch (one host sync per batch)
+constexpr int F0_ARRAYS = 19 + 4;  // arrays in the f[0] allocation: 19 populations + density, jx, jy, jz
 
-std::string g_last_error;
+thread_local std::string g_last_error;  // per thread: several slabs may be driven from threads of one process
+
+// LBG_TIMING=1: host-side phase timings of the set-up entry points on stderr (e2e tuning)
+struct PhaseTimer {
+  bool on;
+  const char* what;
+  double t0, tl;
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+  }
+  explicit PhaseTimer(const char* w) : on(std::getenv("LBG_TIMING") != nullptr), what(w), t0(0), tl(0) {
+    if (on) t0 = tl = now();
+  }
+  void lap(const char* name) {
+    if (!on) return;
+    const double t = now();
+    std::fprintf(stderr, "[lbg timing] %s: %-28s %8.2f ms\n", what, name, (t - tl) * 1e3);
+    tl = t;
+  }
+  ~PhaseTimer() {
+    if (on) std::fprintf(stderr, "[lbg timing] %s: total %8.2f ms\n", what, (now() - t0) * 1e3);
+  }
+};
 
 struct Nccl {
   void* lib = nullptr;
@@ -72,6 +99,15 @@ struct Nccl {
     return GetUniqueId && CommInitRank && CommDestroy && GroupStart && GroupEnd && Send && Recv && AllReduce;
   }
 } g_nccl;
+
+// communicators this process has created (see lbg_comm_init)
+struct CommEntry {
+  int nranks, rank, device;
+  ncclComm_t comm;
+  bool in_use;
+};
+std::mutex g_comm_mu;
+std::vector<CommEntry> g_comms;
 
 struct Force {
   int mode = FORCE_NONE;  // FORCE_NONE / FORCE_UNIFORM / FORCE_FIELD
@@ -115,14 +151,36 @@ struct lbg_handle_s {
   cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   cudaEvent_t ev_ar[2] = {nullptr, nullptr};  // lagged vacf all-reduces of Phase B
   cudaEvent_t ev_arb = nullptr;               // blocking all-reduce on the all-reduce stream
+  cudaEvent_t ev_stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // read-back pipeline (copy_own_to_host_many)
   bool halo_pending = false;
   // peer-to-peer halos (NVLink, copy engines): neighbours' population buffers and arrival flags
   bool p2p = false;
-  double* peer_f[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [down/up][buffer]
+  // Halo planes arrive in a small receive buffer the two ring neighbours map (CUDA IPC) -- mapping the lattices
+  // themselves costs 0.3-0.9 s per 12 GB buffer and handle -- and are copied from there into the halo ranges of
+  // the arrays by a small kernel on the compute stream (halo_unpack_kernel).  Layout, in doubles:
+  // [parity 2][side 2: 0 = from the lower neighbour, 1 = from the upper][array HALO_ARRAYS][halo_cap].
+  double* halo_stage = nullptr;
+  long long halo_cap = 0;
+  double* peer_stage[2] = {nullptr, nullptr};                       // [down/up] neighbour's receive buffer
+  long long peer_cap[2] = {0, 0};
   unsigned int* peer_flags[2] = {nullptr, nullptr};                 // [down/up]
   bool peer_ipc[2] = {false, false};                                // opened with cudaIpcOpenMemHandle
-  long long peer_nfa[2] = {0, 0}, peer_hi_halo[2] = {0, 0};         // neighbour's stride / first fid of its upper halo
-  unsigned int* flags = nullptr;   // [0] = halo data from the lower neighbour has arrived up to this sequence number, [1] = upper
+  struct PendingUnpack {
+    bool on = false;
+    double* base = nullptr;
+    int par = 0, nlo = 0, nhi = 0;
+    int lo_list[5] = {0, 0, 0, 0, 0}, hi_list[5] = {0, 0, 0, 0, 0};
+  } unpack;
+  // `mail` is one small allocation every peer of the job maps: [0..15] 32-bit halo arrival flags (flags[0] = halo data
+  // from the lower neighbour has arrived up to this sequence number, [1] = upper), then from MAIL_OFF (in 64-bit
+  // words) the scalar all-reduce mailbox: 2 parities x nranks senders x MAIL_WORDS words {sequence, payload...}.
+  unsigned long long* mail = nullptr;
+  std::vector<unsigned long long*> peer_mail;   // every rank's mailbox base (own included), host copy
+  std::vector<bool> peer_mail_ipc;
+  unsigned long long** d_peer_mail = nullptr;   // the same on the device
+  unsigned long long ar_seq = 0;                // all-reduces issued so far
+  int comm_slot = -1;                           // entry of the process-wide communicator cache in use (-1: own comm)
+  unsigned int* flags = nullptr;   // = (unsigned int*)mail
   unsigned int xseq = 0;           // exchanges issued so far
   unsigned int xwait = 0;          // sequence number the next kernels must see in flags[]
   int* p2p_err = nullptr;          // set by a wait kernel that timed out
@@ -265,33 +323,82 @@ __global__ void p2p_wait_kernel(const unsigned int* flags, unsigned int seq, Ctr
   __threadfence_system();
 }
 
+constexpr int HALO_ARRAYS = 5;  // arrays per face and exchange: 5 populations (Phase A), 3 (P), 4 (density, momentum)
+
+struct UnpackArgs {
+  const double* stage_lo;  // receive slots of my lower halo (array i at i * cap)
+  const double* stage_hi;
+  double* base;            // arrays of stride nfa
+  long long nfa, cap;
+  long long lo_begin, lo_cnt, hi_begin, hi_cnt;  // fid ranges of my lower / upper halo plane
+  int nlo, nhi;
+  int lo_list[5], hi_list[5];
+};
+
+// receive buffer -> halo ranges of the arrays.  It sits between two steps on the compute stream, so it is
+// spread over the whole GPU: chunks of 4 * BLOCK elements, four independent loads per thread in flight.
+__global__ void __launch_bounds__(BLOCK) halo_unpack_kernel(const __grid_constant__ UnpackArgs a) {
+  constexpr int U = 4;
+  const long long per_lo = (a.lo_cnt + U * BLOCK - 1) / (U * BLOCK), per_hi = (a.hi_cnt + U * BLOCK - 1) / (U * BLOCK);
+  const long long nchunks = a.nlo * per_lo + a.nhi * per_hi;
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const bool lo = c < a.nlo * per_lo;
+    const long long cc = lo ? c : c - a.nlo * per_lo;
+    const long long per = lo ? per_lo : per_hi;
+    const int i = (int)(cc / per);
+    const long long q0 = (cc - (long long)i * per) * (U * BLOCK) + threadIdx.x;
+    const double* src = (lo ? a.stage_lo : a.stage_hi) + (long long)i * a.cap;
+    double* dst = a.base + (long long)(lo ? a.lo_list[i] : a.hi_list[i]) * a.nfa + (lo ? a.lo_begin : a.hi_begin);
+    const long long n = lo ? a.lo_cnt : a.hi_cnt;
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = (q0 + u * BLOCK < n) ? __ldcs(src + q0 + u * BLOCK) : 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (q0 + u * BLOCK < n) dst[q0 + u * BLOCK] = v[u];
+  }
+}
+
+int wait_halo(lbg_handle h);
+
 int halo_exchange_p2p(lbg_handle h, double* base, const int* up_list, int nup, const int* down_list, int ndown) {
   const Geo& g = h->geo;
   const std::vector<long long>& ps = h->pstart;
   const int nz = g.nzl;
-  const int b = (base >= h->f[1] && base < h->f[1] + 19 * g.nfa) ? 1 : 0;
-  const long long base_off = base - h->f[b];                   // offset of the field inside its buffer, in my stride
-  const long long first_arr = base_off / g.nfa;                // fields start on array boundaries
+  if (nup > HALO_ARRAYS || ndown > HALO_ARRAYS) return fail(h, LBG_ERR_INVALID_ARG, "halo exchange: too many arrays");
+  // the previous exchange must have been consumed (its receive slots of the same parity come up again two
+  // exchanges later, and the neighbours may only overwrite them after my unpack: see the header comment)
+  if (h->unpack.on || h->xwait) RET(wait_halo(h));
   const size_t top_cnt = (size_t)(ps[nz + 1] - ps[nz]), bot_cnt = (size_t)(ps[2] - ps[1]);
   CK(cudaEventRecord(h->ev_ready, h->st));
   CK(cudaStreamWaitEvent(h->st_comm, h->ev_ready, 0));
-  for (int i = 0; i < nup && top_cnt; ++i) {   // my top plane -> lower halo of the upper neighbour (its fids 0..)
+  ++h->xseq;
+  const int par = (int)(h->xseq & 1u);
+  for (int i = 0; i < nup && top_cnt; ++i) {   // my top plane -> lower halo of the upper neighbour: its side 0
     const double* src = base + (long long)up_list[i] * g.nfa + ps[nz];
-    double* dst = h->peer_f[1][b] + (first_arr + up_list[i]) * h->peer_nfa[1];
+    double* dst = h->peer_stage[1] + ((long long)(par * 2 + 0) * HALO_ARRAYS + i) * h->peer_cap[1];
     CK(cudaMemcpyAsync(dst, src, top_cnt * sizeof(double), cudaMemcpyDeviceToDevice, h->st_comm));
   }
-  for (int i = 0; i < ndown && bot_cnt; ++i) {  // my bottom plane -> upper halo of the lower neighbour
+  for (int i = 0; i < ndown && bot_cnt; ++i) {  // my bottom plane -> upper halo of the lower neighbour: its side 1
     const double* src = base + (long long)down_list[i] * g.nfa + ps[1];
-    double* dst = h->peer_f[0][b] + (first_arr + down_list[i]) * h->peer_nfa[0] + h->peer_hi_halo[0];
+    double* dst = h->peer_stage[0] + ((long long)(par * 2 + 1) * HALO_ARRAYS + i) * h->peer_cap[0];
     CK(cudaMemcpyAsync(dst, src, bot_cnt * sizeof(double), cudaMemcpyDeviceToDevice, h->st_comm));
   }
-  ++h->xseq;
   // upper neighbour: I am its lower side -> flags[0]; lower neighbour: I am its upper side -> flags[1]
   p2p_signal_kernel<<<1, 1, 0, h->st_comm>>>(h->peer_flags[1] + 0, h->peer_flags[0] + 1, h->xseq);
   h->launches += 1;
   CK(cudaEventRecord(h->ev_halo, h->st_comm));
   h->halo_pending = true;
   h->xwait = h->xseq;
+  // what arrives for me: the lower neighbour's top plane of the up_list arrays, the upper neighbour's bottom
+  // plane of the down_list arrays
+  h->unpack.on = true;
+  h->unpack.base = base;
+  h->unpack.par = par;
+  h->unpack.nlo = nup;
+  h->unpack.nhi = ndown;
+  for (int i = 0; i < nup; ++i) h->unpack.lo_list[i] = up_list[i];
+  for (int i = 0; i < ndown; ++i) h->unpack.hi_list[i] = down_list[i];
   return LBG_OK;
 }
 
@@ -300,8 +407,7 @@ int halo_exchange_p2p(lbg_handle h, double* base, const int* up_list, int nup, c
 // plane goes to the lower neighbour's upper halo.  Runs on st_comm after everything enqueued on st.
 int halo_exchange(lbg_handle h, double* base, const int* up_list, int nup, const int* down_list, int ndown) {
   if (h->nranks == 1) return LBG_OK;
-  if (h->p2p && ((base >= h->f[0] && base < h->f[0] + 19 * h->geo.nfa) || (h->f[1] && base >= h->f[1] && base < h->f[1] + 19 * h->geo.nfa)))
-    return halo_exchange_p2p(h, base, up_list, nup, down_list, ndown);
+  if (h->p2p) return halo_exchange_p2p(h, base, up_list, nup, down_list, ndown);
   const Geo& g = h->geo;
   const std::vector<long long>& ps = h->pstart;
   const int nz = g.nzl;
@@ -336,6 +442,37 @@ int wait_halo(lbg_handle h) {
     h->launches += 1;
     h->xwait = 0;
   }
+  if (h->p2p && h->unpack.on) {  // receive buffer -> halo ranges
+    const std::vector<long long>& ps = h->pstart;
+    const int nz = h->geo.nzl;
+    UnpackArgs a{};
+    a.stage_lo = h->halo_stage + (long long)(h->unpack.par * 2 + 0) * HALO_ARRAYS * h->halo_cap;
+    a.stage_hi = h->halo_stage + (long long)(h->unpack.par * 2 + 1) * HALO_ARRAYS * h->halo_cap;
+    a.base = h->unpack.base;
+    a.nfa = h->geo.nfa;
+    a.cap = h->halo_cap;
+    a.lo_begin = ps[0];
+    a.lo_cnt = ps[1] - ps[0];
+    a.hi_begin = ps[nz + 1];
+    a.hi_cnt = ps[nz + 2] - ps[nz + 1];
+    a.nlo = h->unpack.nlo;
+    a.nhi = h->unpack.nhi;
+    for (int i = 0; i < 5; ++i) {
+      a.lo_list[i] = h->unpack.lo_list[i];
+      a.hi_list[i] = h->unpack.hi_list[i];
+    }
+    const long long nmax = a.lo_cnt > a.hi_cnt ? a.lo_cnt : a.hi_cnt;
+    if (nmax > 0 && a.nlo + a.nhi > 0) {
+      const long long per_lo = (a.lo_cnt + 4 * BLOCK - 1) / (4 * BLOCK), per_hi = (a.hi_cnt + 4 * BLOCK - 1) / (4 * BLOCK);
+      long long gx = a.nlo * per_lo + a.nhi * per_hi;
+      if (gx > 8LL * h->sm_count) gx = 8LL * h->sm_count;
+      if (gx > 0) {
+        halo_unpack_kernel<<<(unsigned)gx, BLOCK, 0, h->st>>>(a);
+        h->launches += 1;
+      }
+    }
+    h->unpack.on = false;
+  }
   return LBG_OK;
 }
 
@@ -351,24 +488,79 @@ int check_p2p(lbg_handle h) {
 const int UP_L[5] = {5, 11, 12, 15, 16};     // cz = +1  (reference l = 6,12,13,16,17)
 const int DOWN_L[5] = {6, 13, 14, 17, 18};   // cz = -1  (reference l = 7,14,15,18,19)
 
-// all-reduce in place across the ring, ordered after st, result visible to st after wait_halo
-// With peer-to-peer halos NCCL is only used for these scalars, on its own stream, so that the copy-engine
-// pushes of the next exchange never queue behind an all-reduce that waits for every rank.
-cudaStream_t ar_stream(const lbg_handle h) { return h->p2p ? h->st_ar : h->st_comm; }
+// ---- scalar all-reduce over peer memory ------------------------------------------------------------------
+// The per-step scalars (l2err + negative flag as a 2-word MAX, vacf[3] as a SUM, counts) are a few words; what
+// an NCCL all-reduce costs there is latency: a stream hand-off, NCCL's kernel, the hand-off back, with the GPU
+// idle in between.  With the peers' mailboxes mapped, ONE small kernel on the compute stream does it: lane r
+// stores this rank's words and then the sequence number into rank r's mailbox (NVLink stores), waits until
+// rank r's words of the same sequence number have landed in its own mailbox, and lane 0 combines the nranks
+// contributions in rank order -- the same order on every rank, so every rank gets the same bits (max is exact
+// anyway; the vacf sum is deterministic and identical everywhere, which the common stop decision needs).
+// Two parities: a rank can be at most one all-reduce ahead of a peer (it needs that peer's contribution to
+// finish the current one), so slot (seq & 1) of all-reduce seq-2 has been consumed before seq overwrites it.
+constexpr int MAIL_OFF = 8;     // 64-bit words reserved in front of the mailbox (halo arrival flags)
+constexpr int MAIL_WORDS = 8;   // {sequence number, up to 7 payload words}
+enum ArOp { AR_U64_MAX = 0, AR_U64_SUM = 1, AR_F64_SUM = 2 };
 
-int allreduce(lbg_handle h, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t op) {
+__global__ void p2p_allreduce_kernel(unsigned long long* const* peer_mail, int nranks, int rank,
+                                     unsigned long long seq, unsigned long long* buf, int n, int op, Ctrl* ctrl,
+                                     int* err) {
+  const int par = (int)(seq & 1ull);
+  for (int r = threadIdx.x; r < nranks; r += blockDim.x) {
+    volatile unsigned long long* slot = peer_mail[r] + MAIL_OFF + ((size_t)par * nranks + rank) * MAIL_WORDS;
+    for (int i = 0; i < n; ++i) slot[1 + i] = buf[i];
+    __threadfence_system();
+    slot[0] = seq;
+  }
+  __threadfence_system();
+  const long long t0 = clock64();
+  for (int r = threadIdx.x; r < nranks; r += blockDim.x) {
+    const volatile unsigned long long* slot = peer_mail[rank] + MAIL_OFF + ((size_t)par * nranks + r) * MAIL_WORDS;
+    while (slot[0] < seq) {
+      if (clock64() - t0 > 40000000000LL) {  // ~20 s: a peer died; give up instead of hanging the GPU
+        ctrl->stop = 1;
+        *err = 3;
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const volatile unsigned long long* base = peer_mail[rank] + MAIL_OFF + (size_t)par * nranks * MAIL_WORDS;
+    for (int i = 0; i < n; ++i) {
+      unsigned long long acc = base[1 + i];
+      for (int r = 1; r < nranks; ++r) {
+        const unsigned long long v = base[(size_t)r * MAIL_WORDS + 1 + i];
+        if (op == AR_U64_MAX) acc = v > acc ? v : acc;
+        else if (op == AR_U64_SUM) acc += v;
+        else acc = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)acc) + __longlong_as_double((long long)v));
+      }
+      buf[i] = acc;
+    }
+  }
+}
+
+// all-reduce in place across the slabs, ordered after st; the result is visible to st after wait_halo.
+// Peer-to-peer mode: one kernel on the compute stream (above).  NCCL mode (LBG_HALO=nccl): ncclAllReduce on the
+// communication stream.
+int allreduce(lbg_handle h, void* buf, size_t n, ArOp op) {
   if (h->nranks == 1) return LBG_OK;
-  cudaStream_t sa = ar_stream(h);
+  if (h->p2p) {
+    if (n > MAIL_WORDS - 1) return fail(h, LBG_ERR_INVALID_ARG, "allreduce: too many words");
+    ++h->ar_seq;
+    p2p_allreduce_kernel<<<1, 32, 0, h->st>>>(h->d_peer_mail, h->nranks, h->rank, h->ar_seq, (unsigned long long*)buf,
+                                              (int)n, (int)op, h->ctrl, h->p2p_err);
+    h->launches += 1;
+    return LBG_OK;
+  }
+  cudaStream_t sa = h->st_comm;
   CK(cudaEventRecord(h->ev_ready, h->st));
   CK(cudaStreamWaitEvent(sa, h->ev_ready, 0));
-  NK(g_nccl.AllReduce(buf, buf, n, dt, op, h->comm, sa));
-  if (h->p2p) {  // blocking use: the compute stream continues once the result is there
-    CK(cudaEventRecord(h->ev_arb, sa));
-    CK(cudaStreamWaitEvent(h->st, h->ev_arb, 0));
-  } else {
-    CK(cudaEventRecord(h->ev_halo, sa));
-    h->halo_pending = true;
-  }
+  NK(g_nccl.AllReduce(buf, buf, n, op == AR_F64_SUM ? ncclDouble : ncclUint64, op == AR_U64_MAX ? ncclMax : ncclSum, h->comm, sa));
+  CK(cudaEventRecord(h->ev_halo, sa));
+  h->halo_pending = true;
   return LBG_OK;
 }
 
@@ -378,9 +570,10 @@ int allreduce(lbg_handle h, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t 
 int ring_barrier(lbg_handle h) {
   if (h->nranks == 1) return LBG_OK;
   CK(cudaMemsetAsync(h->counts, 0, sizeof(unsigned long long), h->st));
-  RET(allreduce(h, h->counts, 1, ncclUint64, ncclSum));
+  RET(allreduce(h, h->counts, 1, AR_U64_SUM));
   RET(wait_halo(h));
   CK(cudaStreamSynchronize(h->st));
+  RET(check_p2p(h));
   return LBG_OK;
 }
 
@@ -410,6 +603,7 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
     return fail(nullptr, LBG_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
   if (device < 0 || device >= ndev) return fail(nullptr, LBG_ERR_INVALID_ARG, "lbg_create: bad device index");
+  PhaseTimer tm("lbg_create");
   h = new lbg_handle_s();
   h->device = device;
   h->geo.lx = lx;
@@ -440,6 +634,7 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   cudaDeviceProp prop;
   CKB(cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
+  tm.lap("device properties");
   CKB(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
   CKB(cudaStreamCreateWithFlags(&h->st_comm, cudaStreamNonBlocking));
   CKB(cudaStreamCreateWithFlags(&h->st_ar, cudaStreamNonBlocking));
@@ -456,6 +651,7 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   CKB(cudaMalloc(&h->ctrl, sizeof(Ctrl)));
   CKB(cudaMalloc(&h->mp_err, sizeof(int)));
   CKB(cudaMalloc(&h->counts, 2 * sizeof(unsigned long long)));
+  tm.lap("streams, events, small device buffers");
   CKB(cudaMallocHost(&h->h_l2, 2 * SLOT_CAP * sizeof(unsigned long long)));
   CKB(cudaMallocHost(&h->h_vacf, 3 * SLOT_CAP * sizeof(double)));
   CKB(cudaMallocHost(&h->h_ctrl, sizeof(Ctrl)));
@@ -468,8 +664,17 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   h->geo.words = h->words;
   int8_t* nat_d = nullptr;
   CKB(cudaMalloc(&nat_d, (size_t)ndense));
-  if (nature_halo) CKB(cudaMemcpyAsync(nat_d, nature_halo, (size_t)ndense, cudaMemcpyHostToDevice, h->st));
-  else h->launches += launch_build_nature(label, lx, ly, lz_global, k0, nzl, nat_d, h->st);
+  tm.lap("pinned host buffers");
+  if (nature_halo && zwrap) {
+    // whole lattice from lbg_create: `nature_halo` holds the lz own planes only
+    CKB(cudaMemcpyAsync(nat_d + plane, nature_halo, (size_t)plane * nzl, cudaMemcpyHostToDevice, h->st));
+    CKB(cudaMemcpyAsync(nat_d, nat_d + plane * nzl, (size_t)plane, cudaMemcpyDeviceToDevice, h->st));
+    CKB(cudaMemcpyAsync(nat_d + plane * (nzl + 1), nat_d + plane, (size_t)plane, cudaMemcpyDeviceToDevice, h->st));
+  } else if (nature_halo) {
+    CKB(cudaMemcpyAsync(nat_d, nature_halo, (size_t)ndense, cudaMemcpyHostToDevice, h->st));
+  } else {
+    h->launches += launch_build_nature(label, lx, ly, lz_global, k0, nzl, nat_d, h->st);
+  }
   h->launches += launch_build_bits((int)plane, nzl, nat_d, h->words, h->nwords, h->st);
   h->launches += launch_scan_ranks(h->words, h->nwords, h->counts, h->st);
   unsigned long long total = 0;
@@ -477,6 +682,7 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   CKB(cudaStreamSynchronize(h->st));
   CKB(cudaGetLastError());
   cudaFree(nat_d);
+  tm.lap("nature H2D + bits + ranks");
   h->nf = (long long)total;
   h->geo.nfa = (h->nf + 31) / 32 * 32;
   if (h->geo.nfa == 0) h->geo.nfa = 32;
@@ -502,11 +708,15 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   CKB(cudaGetLastError());
   h->n_fluid = (int64_t)(own_end(h) - own_begin(h));
   h->n_if_fluid = (int64_t)nif;
+  tm.lap("plane starts + gidx + counts");
 
   // ---- fields
   const size_t nb = (size_t)h->geo.nfa * sizeof(double);
-  CKB(cudaMalloc(&h->f[0], 19 * nb));  // f[1] is allocated when a second lattice is first needed
-  CKB(cudaMalloc(&h->mom, 4 * nb));
+  // f[0] and the moments share one allocation: the ring neighbours map it once (CUDA IPC) and can then push
+  // halo planes of the populations AND of density / momentum (mp_init) straight into it.
+  // f[1] is allocated when a second lattice is first needed.
+  CKB(cudaMalloc(&h->f[0], (size_t)F0_ARRAYS * nb));
+  h->mom = h->f[0] + 19 * h->geo.nfa;
   CKB(cudaMalloc(&h->jpp[0], 3 * nb));
   CKB(cudaMalloc(&h->jpp[1], 3 * nb));
   CKB(cudaMalloc(&h->partial, 3 * (size_t)(h->grid_mp + 8) * sizeof(double)));
@@ -526,6 +736,7 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   h->geo.tpc = h->lb_tpc;
   h->grid_lb = occupancy_grid_lb(h->sm_count, h->lb_minb);
   h->grid_aa = occupancy_grid_aa(h->sm_count);
+  tm.lap("field allocations");
 #undef CKB
   *out = h;
   return LBG_OK;
@@ -587,10 +798,10 @@ int build_strips(lbg_handle h, int p_lo, int p_hi, SegTable* t) {
   return LBG_OK;
 }
 
-int ensure_second_lattice(lbg_handle h) {
+int ensure_second_lattice(lbg_handle h, bool zero = true) {
   if (!h->f[1]) {
     CK(cudaMalloc(&h->f[1], 19 * (size_t)h->geo.nfa * sizeof(double)));
-    CK(cudaMemsetAsync(h->f[1], 0, 19 * (size_t)h->geo.nfa * sizeof(double), h->st));
+    if (zero) CK(cudaMemsetAsync(h->f[1], 0, 19 * (size_t)h->geo.nfa * sizeof(double), h->st));
   }
   return LBG_OK;
 }
@@ -675,6 +886,7 @@ int enqueue_lb_kernel(lbg_handle h, int fin, double tau, const ForceSel& fs, int
   a.target = fl.target;
   a.ctrl = h->ctrl;
   a.pipe = h->lb_pipe;
+  a.neg_flag_local = (h->nranks > 1 && !fl.prev_checked) ? 1 : 0;
   const bool tau1 = (tau == 1.0);
   const std::vector<long long>& ps = h->pstart;
   const int nz = h->geo.nzl;
@@ -696,7 +908,7 @@ int enqueue_lb_kernel(lbg_handle h, int fin, double tau, const ForceSel& fs, int
       // global max of l2err and of the negative-population flag (one all-reduce of the slot pair),
       // before the next step looks at them
       RET(wait_halo(h));
-      RET(allreduce(h, h->l2_slots + 2 * fl.batch_idx, 2, ncclUint64, ncclMax));
+      RET(allreduce(h, h->l2_slots + 2 * fl.batch_idx, 2, AR_U64_MAX));
     }
   }
   return LBG_OK;
@@ -813,11 +1025,30 @@ int snapshot_prev_force(lbg_handle h) {
   return LBG_OK;
 }
 
-// compact array -> the driver's dense (i,j,k) array over the own planes (0 on solid nodes)
-int copy_own_to_host(lbg_handle h, double* dst, const double* arr) {
+// compact arrays -> the driver's dense (i,j,k) arrays over the own planes (0 on solid nodes).
+// The staging buffer holds three dense arrays: the scatter kernel of array i+1 (compute stream) runs while the
+// copy engine moves array i to the host (communication stream).  pull_l >= 0: src[i] is ignored and array i is
+// n(t)(., pull_l + i) rebuilt from the post-collision populations `pull_from` (launch_pull_to_dense).
+int copy_own_to_host_many(lbg_handle h, double* const* dst, const double* const* src, int count,
+                          const double* pull_from = nullptr) {
   RET(ensure_stage(h));
-  h->launches += launch_scatter_to_dense(h->geo, arr, h->stage, h->st);
-  CK(cudaMemcpyAsync(dst, h->stage, (size_t)h->nown * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  for (int e = 0; e < 6; ++e)
+    if (!h->ev_stage[e]) CK(cudaEventCreateWithFlags(&h->ev_stage[e], cudaEventDisableTiming));
+  int issued = 0;
+  for (int i = 0; i < count; ++i) {
+    if (!dst[i]) continue;
+    const int slot = issued % 3;
+    double* stg = h->stage + (size_t)slot * h->nown;
+    if (issued >= 3) CK(cudaStreamWaitEvent(h->st, h->ev_stage[3 + slot], 0));  // the slot's previous copy is done
+    if (pull_from) h->launches += launch_pull_to_dense(h->geo, pull_from, i, stg, h->st);
+    else h->launches += launch_scatter_to_dense(h->geo, src[i], stg, h->st);
+    CK(cudaEventRecord(h->ev_stage[slot], h->st));
+    CK(cudaStreamWaitEvent(h->st_comm, h->ev_stage[slot], 0));
+    CK(cudaMemcpyAsync(dst[i], stg, (size_t)h->nown * sizeof(double), cudaMemcpyDeviceToHost, h->st_comm));
+    CK(cudaEventRecord(h->ev_stage[3 + slot], h->st_comm));
+    ++issued;
+  }
+  CK(cudaStreamSynchronize(h->st_comm));
   CK(cudaStreamSynchronize(h->st));
   return LBG_OK;
 }
@@ -887,14 +1118,9 @@ int lbg_halo_plan(int up[5], int down[5]) {
 int lbg_create(lbg_handle* out, int lx, int ly, int lz, const int8_t* nature, int device) {
   if (!nature || lx < 1 || ly < 1 || lz < 1) return fail(nullptr, LBG_ERR_INVALID_ARG, "lbg_create: invalid argument");
   const size_t plane = (size_t)lx * ly;
-  bool any_fluid = false;
-  for (size_t i = 0; i < plane * lz && !any_fluid; ++i) any_fluid = nature[i] == 0;
-  if (!any_fluid) return fail(nullptr, LBG_ERR_ALL_SOLID, lbg_status_string(LBG_ERR_ALL_SOLID));
-  std::vector<int8_t> nat(plane * ((size_t)lz + 2));
-  std::memcpy(nat.data() + plane, nature, plane * lz);
-  std::memcpy(nat.data(), nature + plane * (lz - 1), plane);               // plane k = -1  == lz-1
-  std::memcpy(nat.data() + plane * ((size_t)lz + 1), nature, plane);       // plane k = lz  == 0
-  return create_common(out, lx, ly, lz, 0, lz, nat.data(), device, true);
+  if (!std::memchr(nature, 0, plane * lz)) return fail(nullptr, LBG_ERR_ALL_SOLID, lbg_status_string(LBG_ERR_ALL_SOLID));
+  // the periodic halo planes (k = -1 == lz-1, k = lz == 0) are copied on the device side of create_common
+  return create_common(out, lx, ly, lz, 0, lz, nature, device, true);
 }
 
 int lbg_create_slab(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nzl, const int8_t* nature_halo,
@@ -935,19 +1161,21 @@ int lbg_destroy(lbg_handle h) {
   if (h->st_comm) cudaStreamSynchronize(h->st_comm);
   if (h->st_ar) cudaStreamSynchronize(h->st_ar);
   for (int s = 0; s < 2; ++s)
-    if (h->peer_ipc[s]) {
-      cudaIpcCloseMemHandle(h->peer_f[s][0]);
-      cudaIpcCloseMemHandle(h->peer_f[s][1]);
-      cudaIpcCloseMemHandle(h->peer_flags[s]);
-    }
-  cudaFree(h->flags);
+    if (h->peer_ipc[s]) cudaIpcCloseMemHandle(h->peer_stage[s]);
+  cudaFree(h->halo_stage);
+  for (size_t r = 0; r < h->peer_mail.size(); ++r)
+    if (h->peer_mail_ipc[r]) cudaIpcCloseMemHandle(h->peer_mail[r]);
+  cudaFree(h->mail);
+  cudaFree(h->d_peer_mail);
   cudaFree(h->p2p_err);
-  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->comm) {  // the communicator stays in the process-wide cache for the next handle
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    if (h->comm_slot >= 0 && (size_t)h->comm_slot < g_comms.size()) g_comms[(size_t)h->comm_slot].in_use = false;
+  }
   cudaFree(h->words);
   cudaFree(h->gidx);
   cudaFree(h->f[0]);
   cudaFree(h->f[1]);
-  cudaFree(h->mom);
   cudaFree(h->jpp[0]);
   cudaFree(h->jpp[1]);
   cudaFree(h->stage);
@@ -968,11 +1196,15 @@ int lbg_destroy(lbg_handle h) {
   if (h->ev_arb) cudaEventDestroy(h->ev_arb);
   if (h->ev_ar[0]) cudaEventDestroy(h->ev_ar[0]);
   if (h->ev_ar[1]) cudaEventDestroy(h->ev_ar[1]);
+  for (int e = 0; e < 6; ++e)
+    if (h->ev_stage[e]) cudaEventDestroy(h->ev_stage[e]);
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
   if (h->st) cudaStreamDestroy(h->st);
   if (h->st_comm) cudaStreamDestroy(h->st_comm);
   if (h->st_ar) cudaStreamDestroy(h->st_ar);
+  // releasing tens of GB is partly deferred by the driver: pay for it here, not in whatever CUDA call comes next
+  cudaDeviceSynchronize();
   delete h;
   return LBG_OK;
 }
@@ -991,44 +1223,76 @@ int lbg_comm_unique_id(void* id_out) {
 int lbg_comm_init(lbg_handle h, int nranks, int rank, const void* id) {
   if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return LBG_ERR_INVALID_ARG;
   if (nranks == 1) return LBG_OK;
+  if (h->comm) return fail(h, LBG_ERR_STATE, "lbg_comm_init: the handle already belongs to a communicator");
   if (h->geo.zwrap) return fail(h, LBG_ERR_STATE, "lbg_comm_init needs a handle made by lbg_create_slab");
   if (h->in_place) return fail(h, LBG_ERR_UNSUPPORTED, "in-place (AA) mode is single-slab only");
   if (!g_nccl.load()) return fail(h, LBG_ERR_NCCL, "cannot load libnccl.so.2");
   CK(cudaSetDevice(h->device));
-  ncclUniqueId uid;
-  std::memcpy(&uid, id, sizeof(uid));
-  NK(g_nccl.CommInitRank(&h->comm, nranks, uid, rank));
+  PhaseTimer tm("lbg_comm_init");
+  // The NCCL communicator is only the bootstrap channel (handle exchange, agreement) and the fallback transport.
+  // Creating one costs seconds on 8 GPUs, so a process keeps the communicators it made and a later handle with
+  // the same (nranks, rank, device) reuses a free one instead of the fresh id (every rank of the job takes the same
+  // decision as long as the ranks create and destroy their handles in the same order; LBG_COMM_CACHE=0 disables).
+  {
+    bool use_cache = true;
+    if (const char* e = std::getenv("LBG_COMM_CACHE")) use_cache = std::atoi(e) != 0;
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    if (use_cache)
+      for (size_t i = 0; i < g_comms.size(); ++i) {
+        CommEntry& c = g_comms[i];
+        if (!c.in_use && c.nranks == nranks && c.rank == rank && c.device == h->device) {
+          c.in_use = true;
+          h->comm = c.comm;
+          h->comm_slot = (int)i;
+          break;
+        }
+      }
+  }
+  if (!h->comm) {
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof(uid));
+    NK(g_nccl.CommInitRank(&h->comm, nranks, uid, rank));
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    g_comms.push_back(CommEntry{nranks, rank, h->device, h->comm, true});
+    h->comm_slot = (int)g_comms.size() - 1;
+  }
+  tm.lap("communicator");
   h->nranks = nranks;
   h->rank = rank;
-  // ---- peer-to-peer halos: map the ring neighbours' population buffers and flags (same node, NVLink)
+  // ---- peer-to-peer: map the ring neighbours' population buffers and every rank's mailbox (same node, NVLink)
   {
     struct PeerInfo {
       int pid, dev;
-      cudaIpcMemHandle_t f0, f1, fl;
-      unsigned long long f0_ptr, f1_ptr, fl_ptr;
-      long long nfa, hi_halo;
+      cudaIpcMemHandle_t hs, ml;
+      unsigned long long hs_ptr, ml_ptr;
+      long long cap;
       int ok;
     };
     int want = 1;
     if (const char* e = std::getenv("LBG_HALO")) want = std::strcmp(e, "nccl") != 0;
-    RET(ensure_second_lattice(h));
-    CK(cudaMalloc(&h->flags, 8 * sizeof(unsigned int)));
-    CK(cudaMemsetAsync(h->flags, 0, 8 * sizeof(unsigned int), h->st));
+    {
+      const std::vector<long long>& ps = h->pstart;
+      const long long lo = ps[1] - ps[0], hi = ps[h->geo.nzl + 2] - ps[h->geo.nzl + 1];
+      h->halo_cap = ((lo > hi ? lo : hi) + 31) / 32 * 32 + 32;
+      CK(cudaMalloc(&h->halo_stage, (size_t)(2 * 2 * HALO_ARRAYS) * (size_t)h->halo_cap * sizeof(double)));
+    }
+    const size_t mail_words = MAIL_OFF + 2 * (size_t)nranks * MAIL_WORDS;
+    CK(cudaMalloc(&h->mail, mail_words * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(h->mail, 0, mail_words * sizeof(unsigned long long), h->st));
+    h->flags = reinterpret_cast<unsigned int*>(h->mail);
     CK(cudaMalloc(&h->p2p_err, sizeof(int)));
     CK(cudaMemsetAsync(h->p2p_err, 0, sizeof(int), h->st));
+    tm.lap("receive buffer + mailbox");
     PeerInfo me{};
     me.pid = (int)getpid();
     me.dev = h->device;
     me.ok = want;
-    if (cudaIpcGetMemHandle(&me.f0, h->f[0]) != cudaSuccess) me.ok = 0;
-    if (cudaIpcGetMemHandle(&me.f1, h->f[1]) != cudaSuccess) me.ok = 0;
-    if (cudaIpcGetMemHandle(&me.fl, h->flags) != cudaSuccess) me.ok = 0;
+    if (cudaIpcGetMemHandle(&me.hs, h->halo_stage) != cudaSuccess) me.ok = 0;
+    if (cudaIpcGetMemHandle(&me.ml, h->mail) != cudaSuccess) me.ok = 0;
     cudaGetLastError();
-    me.f0_ptr = (unsigned long long)h->f[0];
-    me.f1_ptr = (unsigned long long)h->f[1];
-    me.fl_ptr = (unsigned long long)h->flags;
-    me.nfa = h->geo.nfa;
-    me.hi_halo = h->pstart[h->geo.nzl + 1];
+    me.hs_ptr = (unsigned long long)h->halo_stage;
+    me.ml_ptr = (unsigned long long)h->mail;
+    me.cap = h->halo_cap;
     std::vector<PeerInfo> all((size_t)nranks);
     PeerInfo *d_me = nullptr, *d_all = nullptr;
     CK(cudaMalloc(&d_me, sizeof(PeerInfo)));
@@ -1042,43 +1306,65 @@ int lbg_comm_init(lbg_handle h, int nranks, int rank, const void* id) {
     CK(cudaStreamSynchronize(h->st));
     cudaFree(d_me);
     cudaFree(d_all);
+    tm.lap("handle all-gather");
     bool ok = true;
     for (const PeerInfo& p : all) ok = ok && p.ok;
-    const int nbr[2] = {down_rank(h), up_rank(h)};
-    for (int s = 0; s < 2 && ok; ++s) {
-      const PeerInfo& p = all[(size_t)nbr[s]];
-      h->peer_nfa[s] = p.nfa;
-      h->peer_hi_halo[s] = p.hi_halo;
-      if (p.pid == me.pid) {  // several slabs driven from one process: plain peer access
-        if (p.dev != h->device) {
-          cudaError_t e = cudaDeviceEnablePeerAccess(p.dev, 0);
-          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
-          cudaGetLastError();
-        }
-        h->peer_f[s][0] = (double*)p.f0_ptr;
-        h->peer_f[s][1] = (double*)p.f1_ptr;
-        h->peer_flags[s] = (unsigned int*)p.fl_ptr;
-        h->peer_ipc[s] = false;
-      } else if (s == 1 && nbr[1] == nbr[0]) {  // two slabs: the same neighbour on both sides, map once
-        h->peer_f[1][0] = h->peer_f[0][0];
-        h->peer_f[1][1] = h->peer_f[0][1];
-        h->peer_flags[1] = h->peer_flags[0];
-        h->peer_ipc[1] = false;
+    auto enable_peer = [&](int dev) {
+      if (dev == h->device) return true;
+      cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
+      cudaGetLastError();
+      return e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
+    };
+    // every rank's mailbox
+    h->peer_mail.assign((size_t)nranks, nullptr);
+    h->peer_mail_ipc.assign((size_t)nranks, false);
+    for (int r = 0; r < nranks && ok; ++r) {
+      const PeerInfo& p = all[(size_t)r];
+      if (r == rank) {
+        h->peer_mail[(size_t)r] = h->mail;
+      } else if (p.pid == me.pid) {  // several slabs driven from one process: plain peer access
+        ok = enable_peer(p.dev);
+        h->peer_mail[(size_t)r] = (unsigned long long*)p.ml_ptr;
       } else {
-        void *a = nullptr, *b = nullptr, *c = nullptr;
-        if (cudaIpcOpenMemHandle(&a, p.f0, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-            cudaIpcOpenMemHandle(&b, p.f1, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-            cudaIpcOpenMemHandle(&c, p.fl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        void* m = nullptr;
+        if (cudaIpcOpenMemHandle(&m, p.ml, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
           ok = false;
           cudaGetLastError();
         }
-        h->peer_f[s][0] = (double*)a;
-        h->peer_f[s][1] = (double*)b;
-        h->peer_flags[s] = (unsigned int*)c;
-        h->peer_ipc[s] = true;
+        h->peer_mail[(size_t)r] = (unsigned long long*)m;
+        h->peer_mail_ipc[(size_t)r] = m != nullptr;
       }
     }
-    // every rank must take the same path: agree on the outcome
+    tm.lap("mailboxes mapped");
+    const int nbr[2] = {down_rank(h), up_rank(h)};
+    for (int s = 0; s < 2 && ok; ++s) {
+      const PeerInfo& p = all[(size_t)nbr[s]];
+      h->peer_cap[s] = p.cap;
+      h->peer_flags[s] = reinterpret_cast<unsigned int*>(h->peer_mail[(size_t)nbr[s]]);
+      if (p.pid == me.pid) {
+        h->peer_stage[s] = (double*)p.hs_ptr;
+        h->peer_ipc[s] = false;
+      } else if (s == 1 && nbr[1] == nbr[0]) {  // two slabs: the same neighbour on both sides, map once
+        h->peer_stage[1] = h->peer_stage[0];
+        h->peer_ipc[1] = false;
+      } else {
+        void* a = nullptr;
+        if (cudaIpcOpenMemHandle(&a, p.hs, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          ok = false;
+          cudaGetLastError();
+        }
+        h->peer_stage[s] = (double*)a;
+        h->peer_ipc[s] = a != nullptr;
+      }
+    }
+    tm.lap("neighbour receive buffers mapped");
+    if (ok) {
+      CK(cudaMalloc(&h->d_peer_mail, sizeof(unsigned long long*) * (size_t)nranks));
+      CK(cudaMemcpyAsync(h->d_peer_mail, h->peer_mail.data(), sizeof(unsigned long long*) * (size_t)nranks,
+                         cudaMemcpyHostToDevice, h->st));
+    }
+    // every rank must take the same path: agree on the outcome (this all-reduce is also the barrier that
+    // orders every rank's mailbox memset before anybody's first push)
     int* d_ok = h->mp_err;
     int okv = ok ? 1 : 0;
     CK(cudaMemcpyAsync(d_ok, &okv, sizeof(int), cudaMemcpyHostToDevice, h->st));
@@ -1086,14 +1372,15 @@ int lbg_comm_init(lbg_handle h, int nranks, int rank, const void* id) {
     CK(cudaMemcpyAsync(&okv, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     h->p2p = okv != 0;
+    tm.lap("agreement");
   }
   // The LB step kernel is persistent (one wave of resident blocks).  NCCL's send/recv kernel needs SM
   // room to run beside the interior planes' kernel, otherwise the exchange waits for that kernel to end:
   // leave 32 block slots free (measured at N=2: 7.7 -> 6.2 ms per step; profiles/multigpu_r1.txt).
   // The propagate kernel gets the same treatment: its halo exchange and the lagged vacf all-reduce run
   // beside the interior kernel.
-  // With peer-to-peer halos the copy engines move the planes and only the small scalar all-reduces
-  // need an SM, and they run between kernels: nothing is reserved.
+  // With peer-to-peer halos the copy engines move the planes and the scalar all-reduces are one-warp
+  // kernels between the step kernels: nothing is reserved.
   int reserve = h->p2p ? 0 : 32;
   if (const char* e = std::getenv("LBG_GRID_RESERVE")) reserve = std::atoi(e);
   if (reserve > 0 && reserve < h->grid_lb) h->grid_lb -= reserve;
@@ -1385,11 +1672,27 @@ int lbg_lb_step(lbg_handle h, double tau, int nsteps, int check_every, double ta
     if (scr) cudaFree(scr);
     int executed = chunk, conv = 0, neg = 0;
     for (int i = 0; i < chunk; ++i)
-      if (h->h_l2[2 * i + 1]) {  // without a check the flag is local to this slab; with check_every=1 it is global
+      if (h->h_l2[2 * i + 1]) {  // on checked steps the flag is global (it travels with l2err); otherwise this slab's
         executed = i + 1;
         neg = 1;
         break;
       }
+    if (h->nranks > 1 && check_every != 1) {
+      // ANY(n<0) (equilibration.f90:248) is a global test: the slabs agree on the first step that saw a negative
+      // population anywhere (an unchecked step's flag never stopped a kernel, so every rank ran the same steps)
+      unsigned long long w = neg ? (unsigned long long)(chunk - executed + 1) : 0ull;   // larger = earlier step
+      CK(cudaMemcpyAsync(h->counts, &w, sizeof(w), cudaMemcpyHostToDevice, h->st));
+      RET(allreduce(h, h->counts, 1, AR_U64_MAX));
+      RET(wait_halo(h));
+      CK(cudaMemcpyAsync(&w, h->counts, sizeof(w), cudaMemcpyDeviceToHost, h->st));
+      CK(cudaStreamSynchronize(h->st));
+      RET(check_p2p(h));
+      if (w) {
+        const int first = chunk - (int)w + 1;
+        if (first < executed || !neg) executed = first;
+        neg = 1;
+      }
+    }
     for (int i = 0; i < executed; ++i) {
       const long long s = h->t + 1 + i;
       double v = std::numeric_limits<double>::quiet_NaN();
@@ -1433,17 +1736,19 @@ int lbg_lb_download_moments(lbg_handle h, double* rho, double* jx, double* jy, d
   CK(cudaSetDevice(h->device));
   RET(refresh_moments(h, nullptr));
   double* dst[4] = {rho, jx, jy, jz};
-  for (int c = 0; c < 4; ++c)
-    if (dst[c]) RET(copy_own_to_host(h, dst[c], h->mom + (long long)c * h->geo.nfa));
-  return LBG_OK;
+  const double* src[4];
+  for (int c = 0; c < 4; ++c) src[c] = h->mom + (long long)c * h->geo.nfa;
+  RET(wait_halo(h));
+  return copy_own_to_host_many(h, dst, src, 4);
 }
 
 int lbg_lb_download_populations(lbg_handle h, double* n) {
   if (!h || !n) return LBG_ERR_INVALID_ARG;
   if (h->phase != PH_LB) return fail(h, LBG_ERR_STATE, "no Lattice-Boltzmann state");
   CK(cudaSetDevice(h->device));
-  const double* from;
+  const double* from = nullptr;
   double* tmp = nullptr;
+  bool pull = false;
   if (h->in_place) {
     if (!h->aa_swapped) {
       from = h->f[0];  // layout N(t) is the reference's own state
@@ -1455,14 +1760,21 @@ int lbg_lb_download_populations(lbg_handle h, double* n) {
   } else if (h->precollision) {
     from = h->f[h->src];
   } else {
-    // n(t) is rebuilt by a pull from n*(t); the destination buffer is used as scratch
-    RET(refresh_moments(h, h->f[1 - h->src]));
-    h->collided_ok = false;
-    from = h->f[1 - h->src];
+    // n(t) is rebuilt from n*(t) by the pull rule, one direction at a time, straight into the staging buffer:
+    // the stepping state (collided lattice, halo sequence) is not touched, so the call is local to this rank
+    from = h->f[h->src];
+    pull = true;
   }
-  for (int l = 0; l < 19; ++l) RET(copy_own_to_host(h, n + (size_t)l * h->nown, from + (long long)l * h->geo.nfa));
+  double* dst[19];
+  const double* src[19];
+  for (int l = 0; l < 19; ++l) {
+    dst[l] = n + (size_t)l * h->nown;
+    src[l] = from + (long long)l * h->geo.nfa;
+  }
+  RET(wait_halo(h));
+  const int rc = copy_own_to_host_many(h, dst, src, 19, pull ? from : nullptr);
   cudaFree(tmp);
-  return LBG_OK;
+  return rc;
 }
 
 int lbg_lb_profiles(lbg_handle h, int axis, int raw, double* out) {
@@ -1563,7 +1875,7 @@ static int mp_init_impl(lbg_handle h, double Db, double ka, double kd, const dou
   if (h->nranks > 1) {
     unsigned long long c2[2] = {(unsigned long long)nf, (unsigned long long)nif};
     CK(cudaMemcpyAsync(h->counts, c2, sizeof(c2), cudaMemcpyHostToDevice, h->st));
-    RET(allreduce(h, h->counts, 2, ncclUint64, ncclSum));
+    RET(allreduce(h, h->counts, 2, AR_U64_SUM));
     RET(wait_halo(h));
     CK(cudaMemcpyAsync(c2, h->counts, sizeof(c2), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -1626,15 +1938,16 @@ static int mp_init_impl(lbg_handle h, double Db, double ka, double kd, const dou
     for (int d = 0; d < 3; ++d) v0[d] += part[(size_t)b * 3 + d];
   if (h->nranks > 1) {
     CK(cudaMemcpyAsync(h->vacf_slots, v0, sizeof(v0), cudaMemcpyHostToDevice, h->st));
-    RET(allreduce(h, h->vacf_slots, 3, ncclDouble, ncclSum));
+    RET(allreduce(h, h->vacf_slots, 3, AR_F64_SUM));
     RET(wait_halo(h));
     CK(cudaMemcpyAsync(v0, h->vacf_slots, sizeof(v0), cudaMemcpyDeviceToHost, h->st));
-    int badsum = bad;
-    CK(cudaMemcpyAsync(h->mp_err, &badsum, sizeof(int), cudaMemcpyHostToDevice, h->st));
-    RET(allreduce(h, h->mp_err, 1, ncclInt32, ncclMax));
+    unsigned long long badsum = bad ? 1ull : 0ull;
+    CK(cudaMemcpyAsync(h->counts, &badsum, sizeof(badsum), cudaMemcpyHostToDevice, h->st));
+    RET(allreduce(h, h->counts, 1, AR_U64_MAX));
     RET(wait_halo(h));
-    CK(cudaMemcpyAsync(&bad, h->mp_err, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(&badsum, h->counts, sizeof(badsum), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
+    bad = badsum ? 1 : 0;
     // P(now) halo planes for the first step
     const int all3[3] = {0, 1, 2};
     RET(halo_exchange(h, h->P[0], all3, 3, all3, 3));
@@ -1742,15 +2055,15 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
         if (nz > 2) launch(ps[2], ps[nz], true);
         if (lag == 1) {  // blocking variant: the next step waits for this step's global vacf
           RET(wait_halo(h));
-          RET(allreduce(h, h->vacf_slots + 3 * i, 3, ncclDouble, ncclSum));
+          RET(allreduce(h, h->vacf_slots + 3 * i, 3, AR_F64_SUM));
           pc = 1 - pc;
           continue;
         }
         // all-reduce of this step's vacf on the communication stream, not waited for here
         CK(cudaEventRecord(h->ev_ready, h->st));
-        CK(cudaStreamWaitEvent(ar_stream(h), h->ev_ready, 0));
-        NK(g_nccl.AllReduce(h->vacf_slots + 3 * i, h->vacf_slots + 3 * i, 3, ncclDouble, ncclSum, h->comm, ar_stream(h)));
-        CK(cudaEventRecord(h->ev_ar[i & 1], ar_stream(h)));
+        CK(cudaStreamWaitEvent(h->st_comm, h->ev_ready, 0));
+        NK(g_nccl.AllReduce(h->vacf_slots + 3 * i, h->vacf_slots + 3 * i, 3, ncclDouble, ncclSum, h->comm, h->st_comm));
+        CK(cudaEventRecord(h->ev_ar[i & 1], h->st_comm));
       }
       pc = 1 - pc;
     }
@@ -1838,7 +2151,11 @@ int lbg_get_info(lbg_handle h, const char* key, int64_t* value) {
   else if (k == "lb_variant") *value = 100 * h->lb_pipe + 10 * (h->lb_tpc > 0 ? 1 : 0) + h->lb_minb;
   else if (k == "in_place") *value = h->in_place ? 1 : 0;
   else if (k == "p2p") *value = h->p2p ? 1 : 0;
-  else if (k == "ipc") *value = (h->peer_ipc[0] || h->peer_ipc[1]) ? 1 : 0;
+  else if (k == "ipc") {
+    bool any = h->peer_ipc[0] || h->peer_ipc[1];
+    for (size_t r = 0; r < h->peer_mail_ipc.size(); ++r) any = any || h->peer_mail_ipc[r];
+    *value = any ? 1 : 0;
+  }
   else if (k == "nranks") *value = h->nranks;
   else if (k == "rank") *value = h->rank;
   else if (k == "fluid_nodes_with_halo") *value = h->nf;

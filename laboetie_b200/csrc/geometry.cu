@@ -165,6 +165,31 @@ __global__ void __launch_bounds__(BLOCK) gather_from_dense_kernel(Geo geo, const
   }
 }
 
+// n(t)(r, l) of the reference rebuilt from the post-collision populations n*(t) by the pull rule
+// (equilibration.f90:204-243 in closed form, see lb_kernels.cu), written straight into the driver's dense
+// (i,j,k) order for one direction l: a read-back that needs no population-sized scratch and leaves the
+// stepping state untouched.
+__global__ void __launch_bounds__(BLOCK) pull_to_dense_kernel(Geo geo, const double* __restrict__ fin, int l,
+                                                              double* __restrict__ dense) {
+  const long long nown = (long long)geo.plane * geo.nzl;
+  const int X = d3q19::cx(l), Y = d3q19::cy(l), Z = d3q19::cz(l), li = d3q19::inv(l);
+  for (long long q = (long long)blockIdx.x * BLOCK + threadIdx.x; q < nown; q += (long long)gridDim.x * BLOCK) {
+    const int g = (int)(q + geo.plane);
+    int fid;
+    double v = 0.0;
+    if (lookup(geo, g, fid)) {
+      const Nb nb = neighbours(geo, g);
+      // source node r - c_l
+      const int o = (X > 0 ? nb.oxm : (X < 0 ? nb.oxp : 0)) + (Y > 0 ? nb.oym : (Y < 0 ? nb.oyp : 0)) +
+                    (Z > 0 ? nb.ozm : (Z < 0 ? nb.ozp : 0));
+      int fsrc;
+      const bool src_fluid = lookup(geo, g + o, fsrc);
+      v = src_fluid ? fin[(long long)l * geo.nfa + fsrc] : fin[(long long)li * geo.nfa + fid];
+    }
+    dense[q] = v;
+  }
+}
+
 // three SoA arrays -> the reference's AoS (x:z,i,j,k) over the own planes
 __global__ void __launch_bounds__(BLOCK) scatter3_aos_kernel(Geo geo, const double* __restrict__ soa,
                                                              double* __restrict__ aos) {
@@ -283,6 +308,11 @@ int launch_dense_interfacial(const Geo& g, int8_t* out_own, cudaStream_t st) {
 
 int launch_scatter_to_dense(const Geo& g, const double* arr, double* dense_own, cudaStream_t st) {
   scatter_to_dense_kernel<<<big_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, arr, dense_own);
+  return 1;
+}
+
+int launch_pull_to_dense(const Geo& g, const double* fin, int l, double* dense_own, cudaStream_t st) {
+  pull_to_dense_kernel<<<big_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, fin, l, dense_own);
   return 1;
 }
 

@@ -28,7 +28,9 @@ namespace {
 
 __device__ __forceinline__ bool aa_stop_check(const LBArgs& a) {
   int stop = *(volatile int*)&a.ctrl->stop;
-  if (!stop && a.batch_idx > 0 && *(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 1) + 1] != 0ull) {
+  // the flag of step i-1 comes from a moments pass (checked steps), that of step i-2 from kernel i-1 (aa_flag_negative)
+  if (!stop && ((a.batch_idx > 0 && *(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 1) + 1] != 0ull) ||
+                (a.batch_idx > 1 && *(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 2) + 1] != 0ull))) {
     a.ctrl->stop = 1;  // equilibration.f90:248
     stop = 1;
   }
@@ -42,6 +44,14 @@ __device__ __forceinline__ bool aa_stop_check(const LBArgs& a) {
     }
   }
   return stop != 0;
+}
+
+// ANY(n<0) of equilibration.f90:248 without a separate pass: the populations a step kernel reads ARE the state
+// the previous step left behind, so kernel i raises the flag of step i-1 (the first step of a batch looks at a
+// state the previous batch's closing moments pass -- or lbg_lb_init -- has already vetted).  The host then
+// reports exactly the reference's stopping step; rare, so a plain atomic per offending thread.
+__device__ __forceinline__ void aa_flag_negative(const LBArgs& a) {
+  if (a.batch_idx > 0) atomicMax(&a.l2_slots[2 * (a.batch_idx - 1) + 1], 1ull);
 }
 
 template <int FMODE>
@@ -88,7 +98,7 @@ __global__ void __launch_bounds__(BLOCK, 2) aa_even_kernel(const __grid_constant
     double fj[3], fc[3];
     load_forces<FMODE>(a, fid, fj, fc);
     double rho, jx, jy, jz;
-    bool neg;
+    bool neg = false;
     if constexpr (FIRST) {
       rho = mom[fid];
       jx = mom[nfa + fid];
@@ -97,6 +107,7 @@ __global__ void __launch_bounds__(BLOCK, 2) aa_even_kernel(const __grid_constant
     } else {
       moments(n, fj[0] / 2.0, fj[1] / 2.0, fj[2] / 2.0, rho, jx, jy, jz, neg);
     }
+    if (neg) aa_flag_negative(a);
     collide<TAU1, FMODE != FORCE_NONE>(n, a.k, rho, jx, jy, jz, fc[0], fc[1], fc[2], a.w1, a.w2, a.w3);
     static_for<0, NV>([&](auto Lc) {
       constexpr int L = decltype(Lc)::value;
@@ -157,6 +168,7 @@ __global__ void __launch_bounds__(BLOCK, 2) aa_odd_kernel(const __grid_constant_
     double rho, jx, jy, jz;
     bool neg;
     moments(n, fj[0] / 2.0, fj[1] / 2.0, fj[2] / 2.0, rho, jx, jy, jz, neg);
+    if (neg) aa_flag_negative(a);
     collide<TAU1, FMODE != FORCE_NONE>(n, a.k, rho, jx, jy, jz, fc[0], fc[1], fc[2], a.w1, a.w2, a.w3);
     f[fid] = n[0];
     static_for<1, NV>([&](auto Lc) {

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_const
   if (threadIdx.x == 0) {
     // slot pair of a step: [2i] = l2err bits, [2i+1] = non-zero if a population went negative
     int stop = *(volatile int*)&a.ctrl->stop;
-    if (!stop && a.batch_idx > 0 && *(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 1) + 1] != 0ull) {
+    if (!stop && a.batch_idx > 0 && !a.neg_flag_local && *(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 1) + 1] != 0ull) {
       a.ctrl->stop = 1;  // equilibration.f90:248: the reference stops at the step with a negative population
       stop = 1;
     }
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lb_step_pipe_kernel(const __grid_
   __shared__ int s_neg;
   if (threadIdx.x == 0) {
     int stop = *(volatile int*)&a.ctrl->stop;
-    if (!stop && a.batch_idx > 0 && *(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 1) + 1] != 0ull) {
+    if (!stop && a.batch_idx > 0 && !a.neg_flag_local && *(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 1) + 1] != 0ull) {
       a.ctrl->stop = 1;  // equilibration.f90:248
       stop = 1;
     }

@@ -94,6 +94,8 @@ struct LBArgs {
   double target;
   Ctrl* ctrl;
   int pipe;                      // two-stage software pipeline (lb_step_pipe_kernel) instead of the plain kernel
+  int neg_flag_local;            // the previous step's negative-population flag is this slab's only (several slabs, unchecked
+                                 // step): do not stop on it -- the ranks agree on the first such step at the end of the batch
 };
 
 struct CollideArgs {
@@ -224,6 +226,8 @@ int launch_dense_interfacial(const Geo& g, int8_t* out_own, cudaStream_t st);
 // dense <-> compact transfers over own planes (dense index relative to the first own plane)
 int launch_scatter_to_dense(const Geo& g, const double* arr, double* dense_own, cudaStream_t st);
 int launch_gather_from_dense(const Geo& g, const double* dense_own, double* arr, cudaStream_t st);
+// n(t)(., l) pulled from the post-collision populations fin into the dense own-plane order
+int launch_pull_to_dense(const Geo& g, const double* fin, int l, double* dense_own, cudaStream_t st);
 int launch_scatter3_to_dense_aos(const Geo& g, const double* soa3, double* dense_aos_own, cudaStream_t st);
 
 int launch_lb_init(const Geo& g, long long fid_begin, long long fid_end, double rho0, const double a0[3], double* f,
