@@ -206,6 +206,7 @@ struct lbg_handle_s {
   int grid_lb = 148, grid_mp = 148;
   int lb_minb = 2;  // register-allocation variant of the LB step kernel (see lb_kernels.cu)
   int lb_pipe = 1;             // software-pipelined step kernel (lb_kernels.cu lb_step_pipe_kernel)
+  int mp_tpc = 0;              // Phase-B kernel: consecutive tiles per CTA of a grid that covers the tiles (0: persistent grid)
   int lb_tpc = 0;              // tiles per chunk of the dynamic tile schedule of the Phase-A kernels (Geo::tpc; 0 = static)
   int64_t n_fluid = 0, n_if_fluid = 0;  // own planes
 
@@ -237,6 +238,8 @@ struct lbg_handle_s {
   double* s = nullptr;
   double* P[2] = {nullptr, nullptr};
   double* A[2] = {nullptr, nullptr};
+  uint2* awords = nullptr;    // compact adsorbed storage: per group of 32 fids {interfacial bits, first slot} (lbg_internal.h)
+  long long a_stride = 0;     // slots per component of A[.]
   SegTable strips;  // over the planes one propagate launch covers (all own planes, or the interior ones)
 };
 
@@ -719,7 +722,9 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   h->mom = h->f[0] + 19 * h->geo.nfa;
   CKB(cudaMalloc(&h->jpp[0], 3 * nb));
   CKB(cudaMalloc(&h->jpp[1], 3 * nb));
-  CKB(cudaMalloc(&h->partial, 3 * (size_t)(h->grid_mp + 8) * sizeof(double)));
+  // one vacf partial per CTA of a propagate launch: at most one per tile of the slab
+  CKB(cudaMalloc(&h->partial, 3 * ((size_t)(h->geo.nfa / BLOCK) + 2 + (size_t)h->grid_mp + 8) * sizeof(double)));
+  if (const char* e = std::getenv("LBG_MP_TPC")) h->mp_tpc = std::atoi(e) > 0 ? std::atoi(e) : 0;
   // Variant of the Phase-A step kernel (lb_kernels.cu), measured per workload in profiles/ab_r5a.txt:
   //   large slabs: plain kernel, 3 CTAs per SM (80 registers), tiles handed out two at a time by an atomic
   //                counter (cfg5w: 5.44 ms vs 5.70 ms for the static 2-CTA variant);
@@ -1174,6 +1179,7 @@ int lbg_destroy(lbg_handle h) {
   }
   cudaFree(h->words);
   cudaFree(h->gidx);
+  cudaFree(h->awords);
   cudaFree(h->f[0]);
   cudaFree(h->f[1]);
   cudaFree(h->jpp[0]);
@@ -1906,6 +1912,20 @@ static int mp_init_impl(lbg_handle h, double Db, double ka, double kd, const dou
   CK(cudaMemsetAsync(h->f[1], 0, 19 * nb, h->st));
   CK(cudaMemsetAsync(h->mp_err, 0, sizeof(int), h->st));
   CK(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
+  // compact adsorbed storage over the interfacial fluid nodes of the own planes
+  h->a_stride = 0;
+  if (h->ads) {
+    const long long ngroups = g.nfa >> 5;
+    if (!h->awords) CK(cudaMalloc(&h->awords, (size_t)ngroups * sizeof(uint2)));
+    h->launches += launch_build_awords(g, own_begin(h), own_end(h), h->awords, h->st);
+    CK(cudaMemsetAsync(h->counts, 0, sizeof(unsigned long long), h->st));
+    h->launches += launch_scan_ranks(h->awords, ngroups, h->counts, h->st);
+    unsigned long long slots = 0;
+    CK(cudaMemcpyAsync(&slots, h->counts, sizeof(slots), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->a_stride = ((long long)slots + 31) / 32 * 32;
+    if (h->a_stride > g.nfa) return fail(h, LBG_ERR_STATE, "adsorbed storage does not fit");  // cannot happen: slots <= nf + 3 nf / 32... guard anyway
+  }
   MPInitArgs a{};
   a.geo = g;
   a.k = h->k;
@@ -2010,6 +2030,7 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
       MPArgs a{};
       a.geo = g;
       a.geo.tpc = 0;
+      a.tpc = h->mp_tpc;
       a.q = h->q;
       a.nbt01 = h->nbt01;
       a.nbt27 = h->nbt27;
@@ -2019,6 +2040,8 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
       a.Pnext = h->P[1 - pc];
       a.Anow = h->A[pc];
       a.Anext = h->A[1 - pc];
+      a.awords = h->awords;
+      a.a_stride = h->a_stride;
       a.ka = h->ka;
       a.kd = h->kd;
       a.one_minus_kd = 1.0 - h->kd;
@@ -2108,12 +2131,15 @@ int lbg_mp_download(lbg_handle h, double* P, double* Pads) {
   CK(cudaSetDevice(h->device));
   RET(wait_halo(h));
   RET(ensure_stage(h));
-  double* dst[2] = {P, Pads};
-  double* src[2] = {h->P[h->pc], h->A[h->pc]};
-  for (int c = 0; c < 2; ++c) {
-    if (!dst[c]) continue;
-    h->launches += launch_scatter3_to_dense_aos(h->geo, src[c], h->stage, h->st);
-    CK(cudaMemcpyAsync(dst[c], h->stage, (size_t)h->nown * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  if (P) {
+    h->launches += launch_scatter3_to_dense_aos(h->geo, h->P[h->pc], h->stage, h->st);
+    CK(cudaMemcpyAsync(P, h->stage, (size_t)h->nown * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+  }
+  if (Pads) {
+    h->launches += launch_scatter3_compact_to_dense_aos(h->geo, h->ads ? h->awords : nullptr, h->A[h->pc], h->a_stride,
+                                                        h->stage, h->st);
+    CK(cudaMemcpyAsync(Pads, h->stage, (size_t)h->nown * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
   }
   return LBG_OK;

@@ -203,6 +203,44 @@ __global__ void __launch_bounds__(BLOCK) scatter3_aos_kernel(Geo geo, const doub
   }
 }
 
+// compact adsorbed storage (lbg_internal.h): one warp per group of 32 fids
+__global__ void __launch_bounds__(BLOCK) build_awords_kernel(Geo geo, long long fid_begin, long long fid_end,
+                                                             uint2* __restrict__ awords) {
+  const long long ngroups = geo.nfa >> 5;
+  const long long warp0 = ((long long)blockIdx.x * BLOCK + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * BLOCK) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long w = warp0; w < ngroups; w += nwarps) {
+    const long long f = w * 32 + lane;
+    const bool itf = f >= fid_begin && f < fid_end && (geo.gidx[f] & GIDX_INTERFACIAL);
+    const uint32_t b = __ballot_sync(0xffffffffu, itf);
+    if (lane == 0) awords[w] = make_uint2(b, ((uint32_t)__popc(b) + 3u) & ~3u);
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK) scatter3_compact_aos_kernel(Geo geo, const uint2* __restrict__ awords,
+                                                                     const double* __restrict__ a3, long long a_stride,
+                                                                     double* __restrict__ aos) {
+  const long long nown = (long long)geo.plane * geo.nzl;
+  for (long long q = (long long)blockIdx.x * BLOCK + threadIdx.x; q < nown; q += (long long)gridDim.x * BLOCK) {
+    int fid;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+    if (awords && lookup(geo, (int)(q + geo.plane), fid)) {
+      const uint2 w = awords[fid >> 5];
+      const uint32_t bit = (uint32_t)fid & 31u;
+      if ((w.x >> bit) & 1u) {
+        const long long slot = (long long)w.y + __popc(w.x & ((1u << bit) - 1u));
+        v0 = a3[slot];
+        v1 = a3[a_stride + slot];
+        v2 = a3[2 * a_stride + slot];
+      }
+    }
+    aos[3 * q + 0] = v0;
+    aos[3 * q + 1] = v1;
+    aos[3 * q + 2] = v2;
+  }
+}
+
 // supercell_definition.f90:50-59 on the device, for the labels whose thresholds are exact in integer
 // arithmetic: -1 bulk, 1 slit (module_geometry.f90:158-166), 2 cylinder along z (:253-277: solid iff
 // |r - (l+1)/2| >= (lx-1)/2), 3 BCC spheres (:206-245: solid iff the distance to a cube corner or to the
@@ -318,6 +356,17 @@ int launch_pull_to_dense(const Geo& g, const double* fin, int l, double* dense_o
 
 int launch_gather_from_dense(const Geo& g, const double* dense_own, double* arr, cudaStream_t st) {
   gather_from_dense_kernel<<<big_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, dense_own, arr);
+  return 1;
+}
+
+int launch_build_awords(const Geo& g, long long fid_begin, long long fid_end, uint2* awords, cudaStream_t st) {
+  build_awords_kernel<<<big_grid(g.nfa), BLOCK, 0, st>>>(g, fid_begin, fid_end, awords);
+  return 1;
+}
+
+int launch_scatter3_compact_to_dense_aos(const Geo& g, const uint2* awords, const double* a3, long long a_stride,
+                                         double* dense_aos_own, cudaStream_t st) {
+  scatter3_compact_aos_kernel<<<big_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, awords, a3, a_stride, dense_aos_own);
   return 1;
 }
 

@@ -136,20 +136,38 @@ struct MPInitArgs {
   double* partial;     // per block: vacf0 x,y,z
   int* err;            // set if the remaining fraction < eps somewhere
   uint32_t* nbt01;     // neighbour table words 0,1 (stride nfa), see NBT_* below
-  uint32_t* nbt27;     // words 2..7 (stride nfa)
+  uint32_t* nbt27;     // words 2..4 (stride nfa)
 };
 
 // Phase-B neighbour table: the flow AND the geometry are frozen, so the fluid ids of a node's
-// neighbours are static too.  Eight 32-bit words per fluid node, one per neighbouring row
-// (dy,dz) != (0,0):  bits 0..29 = rank position c of the row's centre node (x, y+dy, z+dz) (its fid
-// if it is fluid), bit 31 = centre is fluid.  The x-neighbours of a row follow without a lookup:
-// fid(x+1) = c + centre_fluid, fid(x-1) = c - 1 (if that node is solid the index is a harmless in-range
-// one: its link probability q is 0).  Word 0 bit 30 = "slow": the node sits on the periodic x seam (or
-// an index would leave the arrays) and resolves its neighbours through the rank structure instead
-// (word 2 then holds its dense index g); word 1 bit 30 = interfacial.  32 bytes per node replace gidx (4 bytes) and 18 rank lookups per step.
+// neighbours are static too.  Per fluid node, the rank position c of the centre node (x, y+dy, z+dz) of each of
+// the 8 neighbouring rows (dy,dz) != (0,0) (its fid if it is fluid) and a "centre is fluid" bit.  The
+// x-neighbours of a row follow without a lookup: fid(x+1) = c + centre_fluid, fid(x-1) = c - 1 (if that node is
+// solid the index is a harmless in-range one: its link probability q is 0).
+// Five 32-bit words (20 bytes) per node -- they replace gidx (4 bytes) and 18 rank lookups per step:
+//   word 0: c of row (0,+z), bits 0..29; bit 31 = centre fluid; bit 30 = "slow"
+//   word 1: c of row (0,-z), bits 0..29; bit 31 = centre fluid
+//   word 2: rows (+y,0) | (-y,0) << 16 as 16-bit deltas from the node's own fid
+//   word 3: rows (+y,+z) | (-y,+z) << 16 as 16-bit deltas from word 0's c
+//   word 4: rows (+y,-z) | (-y,-z) << 16 as 16-bit deltas from word 1's c
+// A 16-bit delta is (d + 16384) in bits 0..14 and the row's centre-fluid bit in bit 15: a neighbouring row
+// of the same plane starts at most one row of fluid nodes away.  "Slow" nodes -- on the periodic x or y seam,
+// a delta out of range, or an index that would leave the arrays -- resolve their neighbours through the rank
+// structure instead; word 2 then holds their dense index g.
 constexpr uint32_t NBT_FID_MASK = 0x3fffffffu;
-constexpr uint32_t NBT_FLAG = 0x40000000u;       // word 0: slow, word 1: interfacial
+constexpr uint32_t NBT_FLAG = 0x40000000u;       // word 0: slow
 constexpr uint32_t NBT_CENTRE_FLUID = 0x80000000u;
+constexpr int NBT_DELTA_BIAS = 16384;
+__host__ __device__ constexpr bool nbt_delta_fits(long long d) { return d >= -NBT_DELTA_BIAS && d < NBT_DELTA_BIAS; }
+__host__ __device__ constexpr uint32_t nbt_enc16(int d, bool fluid) {
+  return ((uint32_t)(d + NBT_DELTA_BIAS) & 0x7fffu) | (fluid ? 0x8000u : 0u);
+}
+__host__ __device__ constexpr int nbt_dec16(uint32_t h) { return (int)(h & 0x7fffu) - NBT_DELTA_BIAS; }
+// Adsorbed quantity, stored compactly over the interfacial fluid nodes of the own planes.  For each group of 32
+// consecutive fids: awords[fid >> 5] = { interfacial bits of the 32 nodes, first slot of the group }, slot of a
+// node = first slot + popc(bits below it).  A group's slots are padded to a multiple of 4 (one 32-byte sector
+// per component), so every warp reads and writes whole sectors of its own: 24 + 24 bytes per interfacial node
+// and step (plus padding) instead of a sparse pass over an nfa-sized field.
 // row index of a direction's (cy, cz); -1 for the node's own row
 __host__ __device__ constexpr int nbt_row(int cy, int cz) {
   return cz == 0 ? (cy > 0 ? 0 : (cy < 0 ? 1 : -1))
@@ -174,9 +192,12 @@ struct MPArgs {
   int check_slot;       // evaluate the convergence criterion on this (complete, global) slot, or -1
   double lim;           // 1/(2 lx ly lz / Db)
   Ctrl* ctrl;
-  const uint32_t* nbt01;  // neighbour table (see NBT_*), words 0,1 and 2..7
+  const uint32_t* nbt01;  // neighbour table (see NBT_*), words 0,1 and 2..4
   const uint32_t* nbt27;
+  const uint2* awords;    // compact adsorbed storage (see above); Anow / Anext: 3 components of stride a_stride
+  long long a_stride;
   int use_nbt;            // 0: resolve neighbours through the rank structure (narrow lattices: every warp has seam nodes)
+  int tpc;                // > 0: grid over the tiles, tpc consecutive tiles per CTA; 0: persistent grid, tile-stride loop
   // optional strip order (see SegTable): nseg == 0 means plain fid order over [fid_begin, fid_end)
   int nseg, ntiles;
   const int* tile_cum;          // nseg + 1: tiles before segment k
@@ -229,6 +250,11 @@ int launch_gather_from_dense(const Geo& g, const double* dense_own, double* arr,
 // n(t)(., l) pulled from the post-collision populations fin into the dense own-plane order
 int launch_pull_to_dense(const Geo& g, const double* fin, int l, double* dense_own, cudaStream_t st);
 int launch_scatter3_to_dense_aos(const Geo& g, const double* soa3, double* dense_aos_own, cudaStream_t st);
+// compact adsorbed storage: group words {interfacial bits, padded count} for fids [0, nfa), then launch_scan_ranks
+// turns the counts into first slots; read-back into the reference's AoS order (awords == NULL: all zero)
+int launch_build_awords(const Geo& g, long long fid_begin, long long fid_end, uint2* awords, cudaStream_t st);
+int launch_scatter3_compact_to_dense_aos(const Geo& g, const uint2* awords, const double* a3, long long a_stride,
+                                         double* dense_aos_own, cudaStream_t st);
 
 int launch_lb_init(const Geo& g, long long fid_begin, long long fid_end, double rho0, const double a0[3], double* f,
                    double* mom, cudaStream_t st);

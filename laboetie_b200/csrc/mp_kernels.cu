@@ -132,14 +132,26 @@ __global__ void __launch_bounds__(BLOCK) mp_init_kernel(const __grid_constant__ 
     });
     if (a.ads && (gi & GIDX_INTERFACIAL)) frac = frac - a.ka;  // :240
     if (frac < eps) bad = true;                               // :249
+    // pack: rows (0,+-z) absolute, the others as 16-bit deltas (lbg_internal.h NBT_*)
+    auto cof = [&](int r) { return (long long)(nbw[r] & NBT_FID_MASK); };
+    auto flu = [&](int r) { return (nbw[r] & NBT_CENTRE_FLUID) != 0; };
+    const long long d0 = cof(0) - fid, d1 = cof(1) - fid, d4 = cof(4) - cof(2), d5 = cof(5) - cof(2),
+                    d6 = cof(6) - cof(3), d7 = cof(7) - cof(3);
+    slow = slow || !nbt_delta_fits(d0) || !nbt_delta_fits(d1) || !nbt_delta_fits(d4) || !nbt_delta_fits(d5) ||
+           !nbt_delta_fits(d6) || !nbt_delta_fits(d7);
+    uint32_t pk[5];
+    pk[0] = nbw[2];
+    pk[1] = nbw[3];
+    pk[2] = nbt_enc16((int)d0, flu(0)) | (nbt_enc16((int)d1, flu(1)) << 16);
+    pk[3] = nbt_enc16((int)d4, flu(4)) | (nbt_enc16((int)d5, flu(5)) << 16);
+    pk[4] = nbt_enc16((int)d6, flu(6)) | (nbt_enc16((int)d7, flu(7)) << 16);
     if (slow) {  // such a node resolves all its neighbours through the rank structure: it needs g, not the row centres
-      nbw[0] = NBT_FLAG;
-      nbw[2] = (uint32_t)g;
+      pk[0] = NBT_FLAG;
+      pk[2] = (uint32_t)g;
     }
-    if (gi & GIDX_INTERFACIAL) nbw[1] |= NBT_FLAG;
-    a.nbt01[fid] = nbw[0];
-    a.nbt01[nfa + fid] = nbw[1];
-    for (int r = 2; r < 8; ++r) a.nbt27[(long long)(r - 2) * nfa + fid] = nbw[r];
+    a.nbt01[fid] = pk[0];
+    a.nbt01[nfa + fid] = pk[1];
+    for (int r = 2; r < 5; ++r) a.nbt27[(long long)(r - 2) * nfa + fid] = pk[r];
     a.s[fid] = frac;
     a.s[nfa + fid] = usx;
     a.s[2 * nfa + fid] = usy;
@@ -202,32 +214,58 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
     const long long f = a.seg_begin[k] + (long long)(tile - a.tile_cum[k]) * BLOCK + threadIdx.x;
     return f < a.seg_end[k] ? f : -1;
   };
-  long long f_next = blockIdx.x < ntiles ? node_of(blockIdx.x, seg) : -1;
+  // Tile schedule.  tpc == 0: persistent grid, CTA b visits tiles b, b + gridDim.x, ...  tpc > 0: the grid covers
+  // the tiles, CTA b owns the tpc consecutive tiles from b * tpc -- the hardware block scheduler then balances the
+  // SMs (they do not all get the same share of HBM bandwidth; profiles/streams_r4a.txt) and each stream a CTA
+  // reads is one contiguous run of tpc * 2 KB.
+  const int tile0 = a.tpc > 0 ? (int)blockIdx.x * a.tpc : (int)blockIdx.x;
+  const int tstep = a.tpc > 0 ? 1 : (int)gridDim.x;
+  const int tend = a.tpc > 0 ? (tile0 + a.tpc < ntiles ? tile0 + a.tpc : ntiles) : ntiles;
+  long long f_next = tile0 < tend ? node_of(tile0, seg) : -1;
   // neighbour-table words (NBT) or the dense index (gidx) of the next tile are fetched one iteration
   // ahead: the gathers depend on them
-  uint32_t w_next[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  constexpr int NW = 5;
+  uint32_t w_next[NW] = {0, 0, 0, 0, 0};
+  uint2 aw_next = make_uint2(0u, 0u);
   auto load_words = [&](long long f) {
+    if (a.ads) aw_next = __ldg(a.awords + (f >> 5));
     if constexpr (NBT) {
       w_next[0] = __ldcs(a.nbt01 + f);
       w_next[1] = __ldcs(a.nbt01 + nfa + f);
 #pragma unroll
-      for (int r = 2; r < 8; ++r) w_next[r] = __ldcs(a.nbt27 + (long long)(r - 2) * nfa + f);
+      for (int r = 2; r < NW; ++r) w_next[r] = __ldcs(a.nbt27 + (long long)(r - 2) * nfa + f);
     } else {
       w_next[0] = __ldg(geo.gidx + f);
     }
   };
   if (f_next >= 0) load_words(f_next);
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = tile0; tile < tend; tile += tstep) {
     const long long ff = f_next;
-    const int tn = tile + gridDim.x;
-    uint32_t w[8];
+    const int tn = tile + tstep;
+    uint32_t w[NW];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) w[r] = w_next[r];
-    f_next = tn < ntiles ? node_of(tn, seg) : -1;
+    for (int r = 0; r < NW; ++r) w[r] = w_next[r];
+    const uint2 aw = aw_next;
+    f_next = tn < tend ? node_of(tn, seg) : -1;
     if (f_next >= 0) load_words(f_next);
     if (ff < 0) continue;
     const int fid = (int)ff;
-    const bool adsorbing = a.ads && (NBT ? (w[1] & NBT_FLAG) : (w[0] & GIDX_INTERFACIAL));
+    // adsorbing nodes and their slot in the compact adsorbed arrays: one group word per warp (lbg_internal.h)
+    bool adsorbing = false;
+    long long aslot = 0;
+    int apad = 0;   // padding slots this lane zeroes (whole-sector stores)
+    if (a.ads) {
+      const uint32_t bit = (uint32_t)fid & 31u;
+      adsorbing = (aw.x >> bit) & 1u;
+      const int cnt = __popc(aw.x), below = __popc(aw.x & ((1u << bit) - 1u));
+      if (adsorbing) {
+        aslot = (long long)aw.y + below;
+      } else {  // the k-th non-adsorbing lane of the group zeroes the k-th padding slot
+        const int k = (int)bit - below;
+        apad = k < ((cnt + 3) & ~3) - cnt ? 1 : 0;
+        aslot = (long long)aw.y + cnt + k;
+      }
+    }
     // fluid ids of the 18 neighbours (a solid one -> any in-range id: its q is 0 and adds exactly 0)
     int gp[NV];
     const double* Pn = a.Pnow;
@@ -253,16 +291,33 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
       if (w[0] & NBT_FLAG) {  // periodic x seam (few nodes): through the rank structure, word 2 holds g
         resolve_by_lookup((int)(w[2] & GIDX_MASK));
       } else {
+        // row centres and their "centre is fluid" bits from the packed words
+        int rc[8], rf[8];
+        rc[2] = (int)(w[0] & NBT_FID_MASK);
+        rf[2] = (int)(w[0] >> 31);
+        rc[3] = (int)(w[1] & NBT_FID_MASK);
+        rf[3] = (int)(w[1] >> 31);
+        rc[0] = fid + nbt_dec16(w[2]);
+        rf[0] = (int)((w[2] >> 15) & 1u);
+        rc[1] = fid + nbt_dec16(w[2] >> 16);
+        rf[1] = (int)(w[2] >> 31);
+        rc[4] = rc[2] + nbt_dec16(w[3]);
+        rf[4] = (int)((w[3] >> 15) & 1u);
+        rc[5] = rc[2] + nbt_dec16(w[3] >> 16);
+        rf[5] = (int)(w[3] >> 31);
+        rc[6] = rc[3] + nbt_dec16(w[4]);
+        rf[6] = (int)((w[4] >> 15) & 1u);
+        rc[7] = rc[3] + nbt_dec16(w[4] >> 16);
+        rf[7] = (int)(w[4] >> 31);
         static_for<1, NV>([&](auto Lc) {
           constexpr int L = decltype(Lc)::value;
           constexpr int R = nbt_row(cy(L), cz(L));
           if constexpr (R < 0) {
             gp[L] = fid + cx(L);
           } else {
-            const int c = (int)(w[R] & NBT_FID_MASK);
-            if constexpr (cx(L) == 0) gp[L] = c;
-            else if constexpr (cx(L) > 0) gp[L] = c + (int)(w[R] >> 31);
-            else gp[L] = c - 1;
+            if constexpr (cx(L) == 0) gp[L] = rc[R];
+            else if constexpr (cx(L) > 0) gp[L] = rc[R] + rf[R];
+            else gp[L] = rc[R] - 1;
           }
         });
       }
@@ -279,9 +334,9 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
     const double px = a.Pnow[fid], py = a.Pnow[nfa + fid], pz = a.Pnow[2 * nfa + fid];
     double sx = 0.0, sy = 0.0, sz = 0.0;
     if (adsorbing) {
-      sx = a.Anow[fid];
-      sy = a.Anow[nfa + fid];
-      sz = a.Anow[2 * nfa + fid];
+      sx = __ldcs(a.Anow + aslot);
+      sy = __ldcs(a.Anow + a.a_stride + aslot);
+      sz = __ldcs(a.Anow + 2 * a.a_stride + aslot);
     }
     double ax = 0.0, ay = 0.0, az = 0.0;  // Propagated_Quantity(:,r,next) is always 0 on entry
     static_for<1, NV>([&](auto Lc) {
@@ -294,17 +349,9 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
     vx += px * usx;  // vacf(:,now) += P(:,r,now)*u_star   (:232)
     vy += py * usy;
     vz += pz * usz;
-    // the adsorbed field is written by whole 32-byte sectors (4 consecutive fids): if any node of the
-    // sector adsorbs, its non-adsorbing neighbours store their 0 too, so no sector needs a read-fill
-    bool write_ads = false;
-    if (a.ads) {
-      const unsigned act = __activemask();
-      const unsigned adsb = __ballot_sync(act, adsorbing);
-      const int lane = threadIdx.x & 31;
-      const int l0 = lane - (fid & 3);
-      const unsigned grp = l0 >= 0 ? (0xFu << l0) : (0xFu >> (-l0));
-      write_ads = (adsb & grp) != 0;
-    }
+    // the adsorbed quantity lives in the group's own whole sectors: the adsorbing lanes store their slots, up
+    // to three other lanes store 0 into the padding, so no sector is written partially (no read-fill)
+    const bool write_ads = adsorbing || apad;
     double nx, ny, nz, bx = 0.0, by = 0.0, bz = 0.0;
     if (!adsorbing) {  // :235-238
       nx = ax + frac * px;
@@ -322,9 +369,9 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
     __stcs(a.Pnext + nfa + fid, ny);
     __stcs(a.Pnext + 2 * nfa + fid, nz);
     if (write_ads) {
-      __stcs(a.Anext + fid, bx);
-      __stcs(a.Anext + nfa + fid, by);
-      __stcs(a.Anext + 2 * nfa + fid, bz);
+      __stcs(a.Anext + aslot, bx);
+      __stcs(a.Anext + a.a_stride + aslot, by);
+      __stcs(a.Anext + 2 * a.a_stride + aslot, bz);
     }
   }
   // vacf: block partials, then the last CTA to finish adds them in a fixed order with all its threads (thread t
@@ -376,9 +423,14 @@ int launch_mp_step(const MPArgs& a, int grid, cudaStream_t st) {
   if (a.nseg > 0) {
     if (a.ntiles <= 0) return 0;
     gr = a.ntiles < grid ? a.ntiles : grid;
+    if (a.tpc > 0) gr = (a.ntiles + a.tpc - 1) / a.tpc;
   } else {
     if (a.fid_end <= a.fid_begin) return 0;
     gr = clamp_grid(a.fid_end - a.fid_begin, grid);
+    if (a.tpc > 0) {
+      const long long nt = (a.fid_end - tile_base(a.fid_begin) + BLOCK - 1) / BLOCK;
+      gr = (int)((nt + a.tpc - 1) / a.tpc);
+    }
   }
   if (a.use_nbt) mp_step_kernel<true><<<gr, BLOCK, 0, st>>>(a);
   else mp_step_kernel<false><<<gr, BLOCK, 0, st>>>(a);

@@ -133,6 +133,14 @@ int main() {
       if ((lbg::nbt_row(d3q19::cy(m), d3q19::cz(m)) == r) != (d3q19::cy(m) == d3q19::cy(l) && d3q19::cz(m) == d3q19::cz(l))) ++bad;
   }
   for (int r = 0; r < 8; ++r) if (seen[r] != 1) ++bad;
+  // 16-bit row-centre deltas of the packed table: exact round trip over the whole range, both flag values
+  for (int d = -lbg::NBT_DELTA_BIAS; d < lbg::NBT_DELTA_BIAS; ++d)
+    for (int f = 0; f < 2; ++f) {
+      const uint32_t h = lbg::nbt_enc16(d, f != 0);
+      if (h > 0xffffu || lbg::nbt_dec16(h) != d || (int)((h >> 15) & 1u) != f || !lbg::nbt_delta_fits(d)) ++bad;
+      if (lbg::nbt_dec16((h << 16) >> 16) != d) ++bad;
+    }
+  if (lbg::nbt_delta_fits(lbg::NBT_DELTA_BIAS) || lbg::nbt_delta_fits(-lbg::NBT_DELTA_BIAS - 1)) ++bad;
   printf("%ld\n", bad);
   return bad != 0;
 }

@@ -47,6 +47,30 @@ def build_and_check(nat):
             centre_c[r], centre_f[r] = rank[g], flat[g]
             slow |= (rank[g] < 1) | (rank[g] + 1 >= nfa)
     assert sorted(centre_c) == list(range(8))
+    # packing (lbg_internal.h): rows (0,+-z) absolute, the others 16-bit deltas (+16384, bit 15 = centre fluid)
+    # from the own fid (rows 0, 1), from row 2 (rows 4, 5) and from row 3 (rows 6, 7); out of range -> slow
+    BIAS = 16384
+    ref_of = {0: fid, 1: fid, 4: centre_c[2], 5: centre_c[2], 6: centre_c[3], 7: centre_c[3]}
+    enc = {}
+    for r, ref in ref_of.items():
+        d = centre_c[r].astype(np.int64) - ref.astype(np.int64)
+        slow |= (d < -BIAS) | (d >= BIAS)
+        enc[r] = (((d + BIAS) & 0x7fff) | (centre_f[r].astype(np.int64) << 15)).astype(np.uint32)
+    w = [centre_c[2].astype(np.uint32) | (centre_f[2].astype(np.uint32) << 31),
+         centre_c[3].astype(np.uint32) | (centre_f[3].astype(np.uint32) << 31),
+         enc[0] | (enc[1] << 16), enc[4] | (enc[5] << 16), enc[6] | (enc[7] << 16)]
+    # decode, as mp_step_kernel does
+    dec16 = lambda h: (h & 0x7fff).astype(np.int64) - BIAS     # noqa: E731
+    c2, c3 = (w[0] & 0x3fffffff).astype(np.int64), (w[1] & 0x3fffffff).astype(np.int64)
+    dc = {2: c2, 3: c3, 0: fid + dec16(w[2]), 1: fid + dec16(w[2] >> 16), 4: c2 + dec16(w[3]), 5: c2 + dec16(w[3] >> 16),
+          6: c3 + dec16(w[4]), 7: c3 + dec16(w[4] >> 16)}
+    df = {2: w[0] >> 31, 3: w[1] >> 31, 0: (w[2] >> 15) & 1, 1: w[2] >> 31, 4: (w[3] >> 15) & 1, 5: w[3] >> 31,
+          6: (w[4] >> 15) & 1, 7: w[4] >> 31}
+    for r in range(8):
+        ok = fluid & ~slow
+        assert np.array_equal(dc[r][ok], centre_c[r][ok]) and np.array_equal(df[r][ok].astype(bool), centre_f[r][ok])
+    centre_c = {r: dc[r] for r in range(8)}
+    centre_f = {r: df[r].astype(np.int64) for r in range(8)}
     for l in range(1, 19):
         cx, cy, cz = C[l]
         r = nbt_row(cy, cz)
