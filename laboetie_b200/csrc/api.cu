@@ -241,6 +241,8 @@ struct lbg_handle_s {
   uint2* awords = nullptr;    // compact adsorbed storage: per group of 32 fids {interfacial bits, first slot} (lbg_internal.h)
   long long a_stride = 0;     // slots per component of A[.]
   SegTable strips;  // over the planes one propagate launch covers (all own planes, or the interior ones)
+  SegTable lb_strips;  // the same for the Phase-A step kernel (tiles aligned to 32 fids)
+  bool lb_strips_built = false;
 };
 
 namespace {
@@ -749,17 +751,25 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
 
 // Cut planes [p_lo, p_hi] into strips of rows such that one (strip, plane) segment streams about 16 MB;
 // returns nseg == 0 when a plane is small enough for plain order to keep its neighbours in L2 anyway.
-int build_strips(lbg_handle h, int p_lo, int p_hi, SegTable* t) {
+// aligned: a segment's tiles start on the 32-fid boundary below its first fid (Phase A kernels)
+int build_strips(lbg_handle h, int p_lo, int p_hi, SegTable* t, const char* env = "LBG_MP_STRIP_ROWS", bool aligned = false) {
   t->release();
   const Geo& g = h->geo;
   const int np = p_hi - p_lo + 1;
   if (np < 3) return LBG_OK;
-  const double phi = h->nown > 0 ? (double)h->n_fluid / (double)h->nown : 1.0;
-  // Measured (profiles/variants_r1q.txt): plain fid order is faster on every workload so far -- the
-  // three planes already survive in the 126 MB L2 -- so strips are opt-in (LBG_MP_STRIP_ROWS=<rows>).
-  (void)phi;
+  // Measured (profiles/variants_r1q.txt): plain fid order is faster for the propagate kernel on every workload
+  // so far -- the three planes already survive in the 126 MB L2 -- so strips are opt-in there
+  // (LBG_MP_STRIP_ROWS=<rows>).
   double rows_d = 0;
-  if (const char* e = std::getenv("LBG_MP_STRIP_ROWS")) rows_d = std::atof(e);
+  if (aligned && h->n_fluid > 0 && (double)h->n_if_fluid >= 0.2 * (double)h->n_fluid) {
+    // Phase A on a lattice with many walls: a (strip, plane) segment of about 48 MB of traffic keeps the bounce-back
+    // sectors in L2 until the neighbouring plane's segment reads them (profiles/ab_r5i.txt: -1 % on the porous
+    // benchmark lattice, -5.6 % on Bernoulli noise; +2 % on an all-fluid slit, where it stays off)
+    const double row_fluid = (double)h->n_fluid / ((double)g.nzl * g.ly);
+    rows_d = std::floor(48e6 / (352.0 * (row_fluid > 1 ? row_fluid : 1)) / 8.0) * 8.0;
+    if (rows_d < 16) rows_d = 16;
+  }
+  if (const char* e = std::getenv(env)) rows_d = std::atof(e);
   if (rows_d <= 0 || rows_d >= g.ly) return LBG_OK;
   if (rows_d < 2) rows_d = 2;
   const int rows = (int)rows_d;
@@ -788,7 +798,7 @@ int build_strips(lbg_handle h, int p_lo, int p_hi, SegTable* t) {
       if (e <= b) continue;
       sb.push_back(b);
       se.push_back(e);
-      cum.push_back(cum.back() + (int)((e - b + BLOCK - 1) / BLOCK));
+      cum.push_back(cum.back() + (int)((e - (aligned ? tile_base(b) : b) + BLOCK - 1) / BLOCK));
     }
   if (sb.empty()) return LBG_OK;
   CK(cudaMalloc(&t->tile_cum, cum.size() * sizeof(int)));
@@ -896,19 +906,32 @@ int enqueue_lb_kernel(lbg_handle h, int fin, double tau, const ForceSel& fs, int
   const std::vector<long long>& ps = h->pstart;
   const int nz = h->geo.nzl;
   RET(wait_halo(h));
-  auto launch = [&](long long b, long long e) {
+  auto launch = [&](long long b, long long e, bool use_strips = false) {
     a.fid_begin = b;
     a.fid_end = e;
+    a.nseg = 0;
+    if (use_strips && h->lb_strips.nseg > 0 && !h->lb_pipe) {
+      a.nseg = h->lb_strips.nseg;
+      a.ntiles = h->lb_strips.ntiles;
+      a.tile_cum = h->lb_strips.tile_cum;
+      a.seg_begin = h->lb_strips.seg_begin;
+      a.seg_end = h->lb_strips.seg_end;
+    }
     h->launches += launch_lb_step(a, tau1, fs.mode, fl.check, fl.writej, h->lb_minb, h->grid_lb, h->st);
   };
+  if (!h->lb_strips_built) {  // strip order over the planes the big launch covers (opt-in, LBG_LB_STRIP_ROWS)
+    h->lb_strips_built = true;
+    if (h->nranks == 1) RET(build_strips(h, 1, nz, &h->lb_strips, "LBG_LB_STRIP_ROWS", true));
+    else RET(build_strips(h, 2, nz - 1, &h->lb_strips, "LBG_LB_STRIP_ROWS", true));
+  }
   if (h->nranks == 1) {
-    launch(own_begin(h), own_end(h));
+    launch(own_begin(h), own_end(h), true);
   } else {
     // boundary planes first, so their populations can travel while the interior runs
     launch(ps[1], ps[2]);
     if (nz > 1) launch(ps[nz], ps[nz + 1]);
     RET(halo_exchange(h, h->f[1 - fin], UP_L, 5, DOWN_L, 5));
-    if (nz > 2) launch(ps[2], ps[nz]);
+    if (nz > 2) launch(ps[2], ps[nz], true);
     if (fl.check) {
       // global max of l2err and of the negative-population flag (one all-reduce of the slot pair),
       // before the next step looks at them
@@ -1194,6 +1217,7 @@ int lbg_destroy(lbg_handle h) {
   cudaFree(h->fcur.field);
   cudaFree(h->fprev.field);
   h->strips.release();
+  h->lb_strips.release();
   cudaFreeHost(h->h_l2);
   cudaFreeHost(h->h_vacf);
   cudaFreeHost(h->h_ctrl);

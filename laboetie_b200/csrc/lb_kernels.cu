@@ -106,20 +106,36 @@ __global__ void __launch_bounds__(BLOCK, MINB) lb_step_kernel(const __grid_const
   // tiles of BLOCK consecutive fluid nodes (schedule: lattice.cuh Tiles); the dense index of the next tile's
   // node is fetched one iteration ahead so that its DRAM latency does not sit in front of the dependent
   // population loads
+  // Strip order (a.nseg > 0): the planes are cut into strips of rows and all planes of a strip are visited
+  // before the next strip.  A wall node reads slot inv(l) of ITS OWN fid (bounce-back) while the other nodes of
+  // that 32-byte sector are read, shifted, from the plane above or below; in plain order the two reads are a whole
+  // plane of traffic apart and the sector comes from HBM twice; in strip order they are one (strip, plane)
+  // segment apart and the second read hits L2.
   __shared__ unsigned int s_slot[2];
   Tiles ts;
-  ts.init(geo, a.fid_begin, a.fid_end, &a.ctrl->tile_next, s_slot);
+  ts.init(geo, a.fid_begin, a.fid_end, &a.ctrl->tile_next, s_slot, a.nseg > 0 ? a.ntiles : -1);
   const long long base = tile_base(a.fid_begin) + threadIdx.x;
-  long long ff_next = ts.tile >= 0 ? base + (long long)ts.tile * BLOCK : -1;
-  uint32_t gi_next = (ff_next >= 0 && ff_next < a.fid_end) ? __ldg(geo.gidx + ff_next) : 0u;
+  int seg = 0;
+  auto node_of = [&](int tile) -> long long {  // fid of this thread in `tile`, or -1 (tiles come in increasing order)
+    if (tile < 0) return -1;
+    if (a.nseg == 0) {
+      const long long f = base + (long long)tile * BLOCK;
+      return (f >= a.fid_begin && f < a.fid_end) ? f : -1;
+    }
+    while (tile >= a.tile_cum[seg + 1]) ++seg;
+    const long long sb = a.seg_begin[seg];
+    const long long f = tile_base(sb) + (long long)(tile - a.tile_cum[seg]) * BLOCK + threadIdx.x;
+    return (f >= sb && f < a.seg_end[seg]) ? f : -1;
+  };
+  long long ff_next = node_of(ts.tile);
+  uint32_t gi_next = ff_next >= 0 ? __ldg(geo.gidx + ff_next) : 0u;
   while (ts.tile >= 0) {
     const long long ff = ff_next;
     const uint32_t gi = gi_next;
-    const int tn = ts.next_tile();
-    ff_next = tn >= 0 ? base + (long long)tn * BLOCK : -1;
-    if (ff_next >= 0 && ff_next < a.fid_end) gi_next = __ldg(geo.gidx + ff_next);
+    ff_next = node_of(ts.next_tile());
+    if (ff_next >= 0) gi_next = __ldg(geo.gidx + ff_next);
     ts.advance();
-    if (ff < a.fid_begin || ff >= a.fid_end) continue;
+    if (ff < 0) continue;
     const int fid = (int)ff;
     const int g = (int)(gi & GIDX_MASK);
     const Nb nb = neighbours(geo, g);

@@ -94,6 +94,11 @@ struct LBArgs {
   double target;
   Ctrl* ctrl;
   int pipe;                      // two-stage software pipeline (lb_step_pipe_kernel) instead of the plain kernel
+  // optional strip order of the plain step kernel (see SegTable in api.cu): nseg == 0 means plain fid order
+  int nseg, ntiles;
+  const int* tile_cum;          // nseg + 1: tiles before segment k (a segment's tiles start on its 32-fid boundary)
+  const long long* seg_begin;   // nseg: first fid of segment k
+  const long long* seg_end;     // nseg: one past the last fid of segment k
   int neg_flag_local;            // the previous step's negative-population flag is this slab's only (several slabs, unchecked
                                  // step): do not stop on it -- the ranks agree on the first such step at the end of the batch
 };
