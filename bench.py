@@ -243,7 +243,7 @@ def kernel_source_hash():
     return h.hexdigest()[:16]
 
 
-def verify_launch(dist, rank, nranks, local):
+def verify_launch(dist, rank, nranks, local, in_place=False):
     """Run a small porous lattice through exactly the path this launch uses -- one process per GPU, z-slabs, halos
     pushed through CUDA-IPC-mapped peer memory, scalar all-reduces through the peers' mailboxes -- and compare
     every per-node result with the CPU oracle on rank 0, bit for bit (the oracle is the checker here, nothing of
@@ -261,6 +261,8 @@ def verify_launch(dist, rank, nranks, local):
         uid = [api.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         sim.comm_init(nranks, rank, uid[0])
+    if in_place:
+        sim.lb_set_in_place(True)
     path = "single GPU" if nranks == 1 else ("ipc" if sim.info("ipc") else ("peer" if sim.info("p2p") else "nccl"))
     sim.lb_init(1.0)
     _, _, h1 = sim.lb_step(4, tau=tau, check_every=1, target_error=-1.0)
@@ -296,7 +298,7 @@ def verify_launch(dist, rank, nranks, local):
         scale = np.abs(mp.vacf0).max()      # cross-node sums: to summation order (north_star: 1e-12 relative)
         sum_err = max(float(np.abs(p["v"] - ref_v).max()), float(np.abs(p["v0"] - mp.vacf0).max())) / scale
         ok = ok and sum_err <= 1e-12
-    return {"ok": bool(ok), "max_abs_diff": worst, "vacf_rel_diff": sum_err, "path": path, "lattice": [lx, ly, lz],
+    return {"ok": bool(ok), "phase_a_layout": "in-place (AA)" if in_place else "two-lattice", "max_abs_diff": worst, "vacf_rel_diff": sum_err, "path": path, "lattice": [lx, ly, lz],
             "ranks": nranks, "against": "CPU oracle on rank 0 (bit for bit per node; vacf to 1e-12 relative)",
             "compared": "populations, density, momentum, l2err history (12 LB steps), P, Pads, vacf (8 MP steps)"}
 
@@ -350,13 +352,15 @@ def run_ours(args):
         uid = [api.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         sim.comm_init(nranks, rank, uid[0])
+        if args.in_place:
+            sim.lb_set_in_place(True)
         return sim
 
     # ---- parity of this very launch (process per GPU, IPC halos) against the oracle --------------
     verify = None
     if not args.no_verify:
         try:
-            verify = verify_launch(dist, rank, nranks, local)
+            verify = verify_launch(dist, rank, nranks, local, in_place=args.in_place)
         except Exception as e:  # noqa: BLE001  -- a failed check must show up in the line, not kill the measurement
             verify = {"ok": False, "error": f"{type(e).__name__}: {e}"}
 

@@ -31,7 +31,7 @@
 #include <vector>
 
 #include "../../include/laboetie_gpu.h"
-#include "lbg_internal.h"
+#include "lattice.cuh"
 
 using namespace lbg;
 
@@ -169,6 +169,7 @@ struct lbg_handle_s {
     bool on = false;
     double* base = nullptr;
     int par = 0, nlo = 0, nhi = 0;
+    int reverse = 0;   // 1: the in-place scheme's return trip (masked merge into the own boundary planes)
     int lo_list[5] = {0, 0, 0, 0, 0}, hi_list[5] = {0, 0, 0, 0, 0};
   } unpack;
   // `mail` is one small allocation every peer of the job maps: [0..15] 32-bit halo arrival flags (flags[0] = halo data
@@ -331,13 +332,19 @@ __global__ void p2p_wait_kernel(const unsigned int* flags, unsigned int seq, Ctr
 constexpr int HALO_ARRAYS = 5;  // arrays per face and exchange: 5 populations (Phase A), 3 (P), 4 (density, momentum)
 
 struct UnpackArgs {
-  const double* stage_lo;  // receive slots of my lower halo (array i at i * cap)
-  const double* stage_hi;
+  const double* stage_lo;  // receive slots filled by the lower neighbour (array i at i * cap)
+  const double* stage_hi;  // ... by the upper neighbour
   double* base;            // arrays of stride nfa
   long long nfa, cap;
-  long long lo_begin, lo_cnt, hi_begin, hi_cnt;  // fid ranges of my lower / upper halo plane
+  long long lo_begin, lo_cnt, hi_begin, hi_cnt;  // destination fid ranges: my lower / upper halo plane (forward),
+                                                 // my bottom / top own plane (reverse)
   int nlo, nhi;
   int lo_list[5], hi_list[5];
+  // reverse trip of the in-place (AA) scheme: array m of a boundary-plane node r is taken only if its owner
+  // node r - c_m (in the halo plane, i.e. in the sender's own boundary plane) is fluid -- a slot whose owner is
+  // solid was never written by the sender and holds my own bounce-back value (tests/test_aa_slab_protocol_model.py)
+  int masked;
+  Geo geo;
 };
 
 // receive buffer -> halo ranges of the arrays.  It sits between two steps on the compute stream, so it is
@@ -358,15 +365,37 @@ __global__ void __launch_bounds__(BLOCK) halo_unpack_kernel(const __grid_constan
     double v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) v[u] = (q0 + u * BLOCK < n) ? __ldcs(src + q0 + u * BLOCK) : 0.0;
+    if (!a.masked) {
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (q0 + u * BLOCK < n) dst[q0 + u * BLOCK] = v[u];
+      for (int u = 0; u < U; ++u)
+        if (q0 + u * BLOCK < n) dst[q0 + u * BLOCK] = v[u];
+    } else {
+      const int m = lo ? a.lo_list[i] : a.hi_list[i];
+      const int X = d3q19::cx(m), Y = d3q19::cy(m), Z = d3q19::cz(m);
+      const long long fid0 = lo ? a.lo_begin : a.hi_begin;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long q = q0 + u * BLOCK;
+        if (q >= n) continue;
+        const int g = (int)(a.geo.gidx[fid0 + q] & GIDX_MASK);
+        const Nb nb = neighbours(a.geo, g);
+        const int o = (X > 0 ? nb.oxm : (X < 0 ? nb.oxp : 0)) + (Y > 0 ? nb.oym : (Y < 0 ? nb.oyp : 0)) +
+                      (Z > 0 ? nb.ozm : (Z < 0 ? nb.ozp : 0));
+        int fo;
+        if (lookup(a.geo, g + o, fo)) dst[q] = v[u];
+      }
+    }
   }
 }
 
 int wait_halo(lbg_handle h);
 
-int halo_exchange_p2p(lbg_handle h, double* base, const int* up_list, int nup, const int* down_list, int ndown) {
+// reverse = false: my top own plane of the up_list arrays -> the upper neighbour's lower halo, my bottom own plane of
+// the down_list arrays -> the lower neighbour's upper halo.  reverse = true (in-place scheme after a pull/push
+// step): my upper HALO plane of the up_list arrays -> the upper neighbour's bottom own plane, my lower halo plane of
+// the down_list arrays -> the lower neighbour's top own plane, merged there under the owner mask.
+int halo_exchange_p2p(lbg_handle h, double* base, const int* up_list, int nup, const int* down_list, int ndown,
+                      bool reverse = false) {
   const Geo& g = h->geo;
   const std::vector<long long>& ps = h->pstart;
   const int nz = g.nzl;
@@ -374,18 +403,20 @@ int halo_exchange_p2p(lbg_handle h, double* base, const int* up_list, int nup, c
   // the previous exchange must have been consumed (its receive slots of the same parity come up again two
   // exchanges later, and the neighbours may only overwrite them after my unpack: see the header comment)
   if (h->unpack.on || h->xwait) RET(wait_halo(h));
-  const size_t top_cnt = (size_t)(ps[nz + 1] - ps[nz]), bot_cnt = (size_t)(ps[2] - ps[1]);
+  const long long up_src = reverse ? ps[nz + 1] : ps[nz], down_src = reverse ? ps[0] : ps[1];
+  const size_t top_cnt = (size_t)(reverse ? ps[nz + 2] - ps[nz + 1] : ps[nz + 1] - ps[nz]);
+  const size_t bot_cnt = (size_t)(reverse ? ps[1] - ps[0] : ps[2] - ps[1]);
   CK(cudaEventRecord(h->ev_ready, h->st));
   CK(cudaStreamWaitEvent(h->st_comm, h->ev_ready, 0));
   ++h->xseq;
   const int par = (int)(h->xseq & 1u);
-  for (int i = 0; i < nup && top_cnt; ++i) {   // my top plane -> lower halo of the upper neighbour: its side 0
-    const double* src = base + (long long)up_list[i] * g.nfa + ps[nz];
+  for (int i = 0; i < nup && top_cnt; ++i) {   // -> the upper neighbour: its side 0 (data from its lower neighbour)
+    const double* src = base + (long long)up_list[i] * g.nfa + up_src;
     double* dst = h->peer_stage[1] + ((long long)(par * 2 + 0) * HALO_ARRAYS + i) * h->peer_cap[1];
     CK(cudaMemcpyAsync(dst, src, top_cnt * sizeof(double), cudaMemcpyDeviceToDevice, h->st_comm));
   }
-  for (int i = 0; i < ndown && bot_cnt; ++i) {  // my bottom plane -> upper halo of the lower neighbour: its side 1
-    const double* src = base + (long long)down_list[i] * g.nfa + ps[1];
+  for (int i = 0; i < ndown && bot_cnt; ++i) {  // -> the lower neighbour: its side 1 (data from its upper neighbour)
+    const double* src = base + (long long)down_list[i] * g.nfa + down_src;
     double* dst = h->peer_stage[0] + ((long long)(par * 2 + 1) * HALO_ARRAYS + i) * h->peer_cap[0];
     CK(cudaMemcpyAsync(dst, src, bot_cnt * sizeof(double), cudaMemcpyDeviceToDevice, h->st_comm));
   }
@@ -400,6 +431,7 @@ int halo_exchange_p2p(lbg_handle h, double* base, const int* up_list, int nup, c
   h->unpack.on = true;
   h->unpack.base = base;
   h->unpack.par = par;
+  h->unpack.reverse = reverse ? 1 : 0;
   h->unpack.nlo = nup;
   h->unpack.nhi = ndown;
   for (int i = 0; i < nup; ++i) h->unpack.lo_list[i] = up_list[i];
@@ -410,9 +442,11 @@ int halo_exchange_p2p(lbg_handle h, double* base, const int* up_list, int nup, c
 // Exchange boundary planes with the ring neighbours.  up_list / down_list name the arrays (index into
 // base, stride nfa) whose top own plane goes to the upper neighbour's lower halo / whose bottom own
 // plane goes to the lower neighbour's upper halo.  Runs on st_comm after everything enqueued on st.
-int halo_exchange(lbg_handle h, double* base, const int* up_list, int nup, const int* down_list, int ndown) {
+int halo_exchange(lbg_handle h, double* base, const int* up_list, int nup, const int* down_list, int ndown,
+                  bool reverse = false) {
   if (h->nranks == 1) return LBG_OK;
-  if (h->p2p) return halo_exchange_p2p(h, base, up_list, nup, down_list, ndown);
+  if (h->p2p) return halo_exchange_p2p(h, base, up_list, nup, down_list, ndown, reverse);
+  if (reverse) return fail(h, LBG_ERR_UNSUPPORTED, "the in-place (AA) scheme across slabs needs the peer-to-peer halo transport");
   const Geo& g = h->geo;
   const std::vector<long long>& ps = h->pstart;
   const int nz = g.nzl;
@@ -456,10 +490,19 @@ int wait_halo(lbg_handle h) {
     a.base = h->unpack.base;
     a.nfa = h->geo.nfa;
     a.cap = h->halo_cap;
-    a.lo_begin = ps[0];
-    a.lo_cnt = ps[1] - ps[0];
-    a.hi_begin = ps[nz + 1];
-    a.hi_cnt = ps[nz + 2] - ps[nz + 1];
+    if (!h->unpack.reverse) {
+      a.lo_begin = ps[0];
+      a.lo_cnt = ps[1] - ps[0];
+      a.hi_begin = ps[nz + 1];
+      a.hi_cnt = ps[nz + 2] - ps[nz + 1];
+    } else {
+      a.lo_begin = ps[1];
+      a.lo_cnt = ps[2] - ps[1];
+      a.hi_begin = ps[nz];
+      a.hi_cnt = ps[nz + 1] - ps[nz];
+    }
+    a.masked = h->unpack.reverse;
+    a.geo = h->geo;
     a.nlo = h->unpack.nlo;
     a.nhi = h->unpack.nhi;
     for (int i = 0; i < 5; ++i) {
@@ -1020,6 +1063,7 @@ int refresh_moments(lbg_handle h, double* pops_out) {
     for (int d = 0; d < 3; ++d) a.fj[d] = fj.mode == FORCE_NONE ? 0.0 : fj.u[d];
     a.fj_field = fj.field;
     a.ctrl = h->ctrl;
+    RET(wait_halo(h));
     CK(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
     h->launches += launch_aa_moments(a, fj.mode, h->aa_swapped, false, false, h->mom, pops_out, h->grid_aa, h->st);
     h->mom_valid_step = h->t;
@@ -1255,7 +1299,6 @@ int lbg_comm_init(lbg_handle h, int nranks, int rank, const void* id) {
   if (nranks == 1) return LBG_OK;
   if (h->comm) return fail(h, LBG_ERR_STATE, "lbg_comm_init: the handle already belongs to a communicator");
   if (h->geo.zwrap) return fail(h, LBG_ERR_STATE, "lbg_comm_init needs a handle made by lbg_create_slab");
-  if (h->in_place) return fail(h, LBG_ERR_UNSUPPORTED, "in-place (AA) mode is single-slab only");
   if (!g_nccl.load()) return fail(h, LBG_ERR_NCCL, "cannot load libnccl.so.2");
   CK(cudaSetDevice(h->device));
   PhaseTimer tm("lbg_comm_init");
@@ -1302,8 +1345,10 @@ int lbg_comm_init(lbg_handle h, int nranks, int rank, const void* id) {
     if (const char* e = std::getenv("LBG_HALO")) want = std::strcmp(e, "nccl") != 0;
     {
       const std::vector<long long>& ps = h->pstart;
-      const long long lo = ps[1] - ps[0], hi = ps[h->geo.nzl + 2] - ps[h->geo.nzl + 1];
-      h->halo_cap = ((lo > hi ? lo : hi) + 31) / 32 * 32 + 32;
+      const int nzq = h->geo.nzl;
+      long long m = 0;  // halo planes (forward trips) and own boundary planes (return trip of the in-place scheme)
+      for (long long c : {ps[1] - ps[0], ps[nzq + 2] - ps[nzq + 1], ps[2] - ps[1], ps[nzq + 1] - ps[nzq]}) m = c > m ? c : m;
+      h->halo_cap = (m + 31) / 32 * 32 + 32;
       CK(cudaMalloc(&h->halo_stage, (size_t)(2 * 2 * HALO_ARRAYS) * (size_t)h->halo_cap * sizeof(double)));
     }
     const size_t mail_words = MAIL_OFF + 2 * (size_t)nranks * MAIL_WORDS;
@@ -1532,6 +1577,24 @@ int lbg_lb_time(lbg_handle h, int64_t* t) {
   return LBG_OK;
 }
 
+// ANY(n<0) (equilibration.f90:248) is a global test: the slabs agree on the first step of the batch that saw a
+// negative population anywhere (an unchecked step's flag never stopped a kernel, so every rank ran the same steps)
+static int agree_on_negative_step(lbg_handle h, int chunk, int* executed, int* neg) {
+  unsigned long long w = *neg ? (unsigned long long)(chunk - *executed + 1) : 0ull;   // larger = earlier step
+  CK(cudaMemcpyAsync(h->counts, &w, sizeof(w), cudaMemcpyHostToDevice, h->st));
+  RET(allreduce(h, h->counts, 1, AR_U64_MAX));
+  RET(wait_halo(h));
+  CK(cudaMemcpyAsync(&w, h->counts, sizeof(w), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  RET(check_p2p(h));
+  if (w) {
+    const int first = chunk - (int)w + 1;
+    if (first < *executed || !*neg) *executed = first;
+    *neg = 1;
+  }
+  return LBG_OK;
+}
+
 // In-place (AA) stepping, see lb_aa_kernels.cu.  One kernel per step, plus a moments pass on the steps
 // whose l2err is asked for (and after the last step of a call, for the negative-population guard).
 static int lb_step_in_place(lbg_handle h, double tau, int nsteps, int check_every, double target_error,
@@ -1580,6 +1643,7 @@ static int lb_step_in_place(lbg_handle h, double tau, int nsteps, int check_ever
         LBArgs a = base_args(fl);
         a.l2_slots = nullptr;
         a.jnew = h->jpp[h->jc];
+        RET(wait_halo(h));
         h->launches += launch_aa_moments(a, fl.mode, h->aa_swapped, false, true, nullptr, nullptr, h->grid_aa, h->st);
       }
       h->j_valid_step = h->t;
@@ -1594,7 +1658,29 @@ static int lb_step_in_place(lbg_handle h, double tau, int nsteps, int check_ever
       a.prev_checked = (i > 0 && checked(s - 1)) ? 1 : 0;
       a.prev_may_stop = (s - 1 > 2) ? 1 : 0;
       const bool first = h->precollision && i == 0;
-      h->launches += launch_aa_step(a, tau == 1.0, fs.mode, swapped, first, h->mom, h->grid_aa, h->st);
+      a.neg_flag_local = h->nranks > 1 ? (a.prev_checked ? 2 : 1) : 0;
+      RET(wait_halo(h));
+      if (h->nranks == 1) {
+        h->launches += launch_aa_step(a, tau == 1.0, fs.mode, swapped, first, h->mom, h->grid_aa, h->st);
+      } else {
+        // Across slabs (tests/test_aa_slab_protocol_model.py): boundary planes first, then their exchange runs
+        // beside the interior planes' kernel.  After a local step (N -> S) slot inv(l) holds direction l, so the top
+        // plane's cz = -1 slots feed the upper neighbour's pull and the bottom plane's cz = +1 slots the lower
+        // one's (the two-lattice lists, swapped).  After a pull/push step (S -> N) the pushes that landed in my
+        // halo planes travel back into the neighbours' boundary planes, merged there under the owner mask.
+        const std::vector<long long>& ps = h->pstart;
+        const int nz = h->geo.nzl;
+        auto launch = [&](long long b, long long e) {
+          a.fid_begin = b;
+          a.fid_end = e;
+          h->launches += launch_aa_step(a, tau == 1.0, fs.mode, swapped, first, h->mom, h->grid_aa, h->st);
+        };
+        launch(ps[1], ps[2]);
+        if (nz > 1) launch(ps[nz], ps[nz + 1]);
+        if (!swapped) RET(halo_exchange(h, h->f[0], DOWN_L, 5, UP_L, 5));
+        else RET(halo_exchange(h, h->f[0], UP_L, 5, DOWN_L, 5, true));
+        if (nz > 2) launch(ps[2], ps[nz]);
+      }
       swapped = !swapped;
       const bool chk = checked(s), wj = chk || checked(s + 1), last = (i == chunk - 1);
       if (chk || wj || last) {
@@ -1602,13 +1688,17 @@ static int lb_step_in_place(lbg_handle h, double tau, int nsteps, int check_ever
         m.batch_idx = i;
         m.jold = h->jpp[jold];
         m.jnew = h->jpp[1 - jold];
+        RET(wait_halo(h));   // the S layout is read through the halo planes; the N layout needs the merged return trip
         h->launches += launch_aa_moments(m, fs_rest.mode, swapped, chk, wj, nullptr, nullptr, h->grid_aa, h->st);
+        if (chk && h->nranks > 1) RET(allreduce(h, h->l2_slots + 2 * i, 2, AR_U64_MAX));
       }
       jold = 1 - jold;
     }
+    RET(wait_halo(h));
     CK(cudaMemcpyAsync(h->h_l2, h->l2_slots, 2 * (size_t)chunk * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     CK(cudaGetLastError());
+    RET(check_p2p(h));
     cudaFree(scr_j);
     if (scr_c != scr_j) cudaFree(scr_c);
     int executed = chunk, conv = 0, neg = 0;
@@ -1618,6 +1708,7 @@ static int lb_step_in_place(lbg_handle h, double tau, int nsteps, int check_ever
         neg = 1;
         break;
       }
+    if (h->nranks > 1 && check_every != 1) RET(agree_on_negative_step(h, chunk, &executed, &neg));
     for (int i = 0; i < executed; ++i) {
       const long long s = h->t + 1 + i;
       double v = std::numeric_limits<double>::quiet_NaN();
@@ -1654,7 +1745,8 @@ static int lb_step_in_place(lbg_handle h, double tau, int nsteps, int check_ever
 
 int lbg_lb_set_in_place(lbg_handle h, int on) {
   if (!h) return LBG_ERR_INVALID_ARG;
-  if (on && h->nranks > 1) return fail(h, LBG_ERR_UNSUPPORTED, "in-place (AA) mode is single-slab only");
+  if (on && h->nranks > 1 && !h->p2p)
+    return fail(h, LBG_ERR_UNSUPPORTED, "in-place (AA) mode across slabs needs the peer-to-peer halo transport");
   h->in_place = on != 0;
   h->phase = PH_CREATED;  // takes effect with the next lbg_lb_init / lbg_lb_upload
   return LBG_OK;
@@ -1707,22 +1799,7 @@ int lbg_lb_step(lbg_handle h, double tau, int nsteps, int check_every, double ta
         neg = 1;
         break;
       }
-    if (h->nranks > 1 && check_every != 1) {
-      // ANY(n<0) (equilibration.f90:248) is a global test: the slabs agree on the first step that saw a negative
-      // population anywhere (an unchecked step's flag never stopped a kernel, so every rank ran the same steps)
-      unsigned long long w = neg ? (unsigned long long)(chunk - executed + 1) : 0ull;   // larger = earlier step
-      CK(cudaMemcpyAsync(h->counts, &w, sizeof(w), cudaMemcpyHostToDevice, h->st));
-      RET(allreduce(h, h->counts, 1, AR_U64_MAX));
-      RET(wait_halo(h));
-      CK(cudaMemcpyAsync(&w, h->counts, sizeof(w), cudaMemcpyDeviceToHost, h->st));
-      CK(cudaStreamSynchronize(h->st));
-      RET(check_p2p(h));
-      if (w) {
-        const int first = chunk - (int)w + 1;
-        if (first < executed || !neg) executed = first;
-        neg = 1;
-      }
-    }
+    if (h->nranks > 1 && check_every != 1) RET(agree_on_negative_step(h, chunk, &executed, &neg));
     for (int i = 0; i < executed; ++i) {
       const long long s = h->t + 1 + i;
       double v = std::numeric_limits<double>::quiet_NaN();

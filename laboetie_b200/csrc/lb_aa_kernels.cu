@@ -29,8 +29,11 @@ namespace {
 __device__ __forceinline__ bool aa_stop_check(const LBArgs& a) {
   int stop = *(volatile int*)&a.ctrl->stop;
   // the flag of step i-1 comes from a moments pass (checked steps), that of step i-2 from kernel i-1 (aa_flag_negative)
-  if (!stop && ((a.batch_idx > 0 && *(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 1) + 1] != 0ull) ||
-                (a.batch_idx > 1 && *(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 2) + 1] != 0ull))) {
+  // (across slabs a flag only counts once it is global: neg_flag_local 1 = neither is, 2 = only that of step i-1)
+  if (!stop && ((a.batch_idx > 0 && a.neg_flag_local != 1 &&
+                 *(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 1) + 1] != 0ull) ||
+                (a.batch_idx > 1 && a.neg_flag_local == 0 &&
+                 *(volatile unsigned long long*)&a.l2_slots[2 * (a.batch_idx - 2) + 1] != 0ull))) {
     a.ctrl->stop = 1;  // equilibration.f90:248
     stop = 1;
   }

@@ -17,9 +17,12 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 v = bench.verify_launch(dist, rank, world, local)
 # a second handle in the same processes: the cached communicator is reused, results must not change
 v2 = bench.verify_launch(dist, rank, world, local)
+# Phase A in place (AA pattern) across the slabs
+v3 = bench.verify_launch(dist, rank, world, local, in_place=True)
 if rank == 0:
     v["second_run_ok"] = bool(v2["ok"])
-    v["ok"] = bool(v["ok"] and v2["ok"])
+    v["in_place_ok"] = bool(v3["ok"])
+    v["ok"] = bool(v["ok"] and v2["ok"] and v3["ok"])
     print(json.dumps(v))
 dist.barrier()
 dist.destroy_process_group()

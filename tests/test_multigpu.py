@@ -43,8 +43,9 @@ def _run_ranks(nranks, fn):
 
 @pytest.mark.parametrize("shape,nranks", [((16, 12, 21), 2), ((1, 9, 14), 2), ((33, 5, 8), 2), ((8, 8, 9), 4),
                                           ((6, 5, 10, "slit"), 2)])
-@pytest.mark.parametrize("tau,nbt", [(1.0, "0"), (0.8, "1")])
-def test_slabs_match_single_gpu(shape, nranks, tau, nbt, monkeypatch):
+@pytest.mark.parametrize("tau,nbt,in_place", [(1.0, "0", False), (0.8, "1", False), (0.8, "1", True), (1.0, "0", True)],
+                         ids=["tau1-lookups", "tau0.8-table", "tau0.8-table-in-place", "tau1-lookups-in-place"])
+def test_slabs_match_single_gpu(shape, nranks, tau, nbt, in_place, monkeypatch):
     import laboetie_b200 as lb
     from laboetie_b200 import api, slab
     if _ndev() < nranks:
@@ -75,6 +76,8 @@ def test_slabs_match_single_gpu(shape, nranks, tau, nbt, monkeypatch):
     def rank_fn(r):
         sim = slab.make_slab_sim(nat, r, nranks, device=r, unique_id=uid)
         try:
+            if in_place:    # AA pattern across the slabs: forward exchange after the local step, masked return trip
+                sim.lb_set_in_place(True)
             sim.lb_init(1.0)
             _, _, g1 = sim.lb_step(4, tau=tau, check_every=1, target_error=-1.0)
             sim.lb_set_force_uniform(f)
@@ -84,6 +87,8 @@ def test_slabs_match_single_gpu(shape, nranks, tau, nbt, monkeypatch):
             prof_z = sim.lb_profiles(2)
             prof_xy = [sim.lb_profiles(a, raw=True) for a in (0, 1)]
             sim.lb_step(2, tau=tau, check_every=0)
+            if in_place:
+                assert sim.info("in_place") == 1
             v0 = sim.mp_init(Db, ka, kd, f)
             _, _, v = sim.mp_step(9)
             P, A = sim.mp_download()

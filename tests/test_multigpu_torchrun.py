@@ -22,9 +22,10 @@ def _ndev():
     return n.value
 
 
-def test_verify_launch_single_gpu():
+@pytest.mark.parametrize("in_place", [False, True])
+def test_verify_launch_single_gpu(in_place):
     import bench
-    v = bench.verify_launch(None, 0, 1, 0)
+    v = bench.verify_launch(None, 0, 1, 0, in_place=in_place)
     assert v["ok"] and v["max_abs_diff"] == 0.0 and v["path"] == "single GPU", v
 
 
@@ -39,3 +40,4 @@ def test_process_per_gpu_matches_oracle(nranks):
     assert out.returncode == 0, out.stderr[-3000:]
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert line["ok"] and line["max_abs_diff"] == 0.0 and line["path"] == "ipc" and line["ranks"] == nranks, line
+    assert line["second_run_ok"] and line["in_place_ok"], line
