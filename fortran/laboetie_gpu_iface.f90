@@ -15,6 +15,7 @@ module laboetie_gpu
   public :: lbg_get_interfacial, lbg_get_counts
   public :: lbg_lb_set_in_place, lbg_lb_init, lbg_lb_upload, lbg_lb_set_force_uniform, lbg_lb_set_force_field, lbg_lb_step, lbg_lb_time
   public :: lbg_lb_download_moments, lbg_lb_download_populations, lbg_lb_profiles, lbg_lb_total_flux, lbg_lb_probe
+  public :: lbg_lb_download_moments_async, lbg_wait_transfers, lbg_get_info
   public :: lbg_mp_init, lbg_mp_init_from_moments, lbg_mp_step, lbg_mp_download, lbg_sync, lbg_status_message
 
   integer(c_int), parameter, public :: LBG_OK = 0
@@ -118,6 +119,22 @@ module laboetie_gpu
       import :: c_ptr, c_int, c_double
       type(c_ptr), value :: h
       real(c_double), intent(out) :: rho(*), jx(*), jy(*), jz(*)
+    end function
+    ! the same read-back, queued: rho, jx, jy, jz are valid after lbg_wait_transfers (Phase B may run meanwhile)
+    integer(c_int) function lbg_lb_download_moments_async(h, rho, jx, jy, jz) bind(C, name="lbg_lb_download_moments_async")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      real(c_double), intent(out) :: rho(*), jx(*), jy(*), jz(*)
+    end function
+    integer(c_int) function lbg_wait_transfers(h) bind(C, name="lbg_wait_transfers")
+      import :: c_ptr, c_int
+      type(c_ptr), value :: h
+    end function
+    integer(c_int) function lbg_get_info(h, key, val) bind(C, name="lbg_get_info")
+      import :: c_ptr, c_int, c_char, c_int64_t
+      type(c_ptr), value :: h
+      character(kind=c_char), intent(in) :: key(*)       ! NUL-terminated, e.g. "mp_neighbour_table"//c_null_char
+      integer(c_int64_t), intent(out) :: val
     end function
     integer(c_int) function lbg_lb_download_populations(h, n) bind(C, name="lbg_lb_download_populations")
       import :: c_ptr, c_int, c_double

@@ -133,6 +133,12 @@ int lbg_lb_step(lbg_handle h, double tau, int nsteps, int check_every, double ta
 int lbg_lb_time(lbg_handle h, int64_t* t);
 /* equilibration.f90:551-554: density and momentum density after the last step (own planes). */
 int lbg_lb_download_moments(lbg_handle h, double* rho, double* jx, double* jy, double* jz);
+/* The same read-back without waiting for it: the call returns once the work is queued (the four host arrays
+ * should be page-locked, otherwise the copies are synchronous anyway) and the arrays are valid after
+ * lbg_wait_transfers.  Density and momentum stay resident, so the driver can go on with lbg_mp_init /
+ * lbg_mp_step -- the reference's drop_tracers phase -- while 32 bytes per node cross PCIe. */
+int lbg_lb_download_moments_async(lbg_handle h, double* rho, double* jx, double* jy, double* jz);
+int lbg_wait_transfers(lbg_handle h);
 /* system::n after the last completed step (parity / debugging; own planes). */
 int lbg_lb_download_populations(lbg_handle h, double* n);
 /* equilibration.f90:161-172,505-516: for each index p along axis (0=x,1=y,2=z)

@@ -26,7 +26,7 @@ SYMBOLS = [
     "lbg_abi_version", "lbg_status_string", "lbg_last_error", "lbg_device_count", "lbg_partition", "lbg_halo_plan",
     "lbg_create", "lbg_create_slab", "lbg_create_geometry", "lbg_get_nature", "lbg_destroy", "lbg_comm_unique_id", "lbg_comm_init", "lbg_get_interfacial",
     "lbg_get_counts", "lbg_lb_set_in_place", "lbg_lb_init", "lbg_lb_upload", "lbg_lb_set_force_uniform", "lbg_lb_set_force_field",
-    "lbg_lb_step", "lbg_lb_time", "lbg_lb_download_moments", "lbg_lb_download_populations", "lbg_lb_profiles",
+    "lbg_lb_step", "lbg_lb_time", "lbg_lb_download_moments", "lbg_lb_download_moments_async", "lbg_wait_transfers", "lbg_lb_download_populations", "lbg_lb_profiles",
     "lbg_lb_total_flux", "lbg_lb_probe", "lbg_mp_init", "lbg_mp_init_from_moments", "lbg_mp_step", "lbg_mp_download", "lbg_timer_start",
     "lbg_timer_stop", "lbg_launch_count", "lbg_get_info", "lbg_sync",
 ]
@@ -80,6 +80,8 @@ def load_library():
     L.lbg_lb_step.argtypes = [P, D, I, I, D, P, C.POINTER(I), C.POINTER(I)]
     L.lbg_lb_time.argtypes = [P, C.POINTER(C.c_int64)]
     L.lbg_lb_download_moments.argtypes = [P, f64, f64, f64, f64]
+    L.lbg_lb_download_moments_async.argtypes = [P, f64, f64, f64, f64]
+    L.lbg_wait_transfers.argtypes = [P]
     L.lbg_lb_download_populations.argtypes = [P, f64]
     L.lbg_lb_profiles.argtypes = [P, I, I, f64]
     L.lbg_lb_total_flux.argtypes = [P, f64]
@@ -265,6 +267,16 @@ class LaboetieGPU:
         out = [np.zeros(self.shape) for _ in range(4)]
         self._ck(self._L.lbg_lb_download_moments(self._h, *out))
         return out
+
+    def lb_moments_async(self, out):
+        """Queue the read-back of density and momentum into the four (preferably pinned) arrays `out`; they are
+        valid after wait_transfers().  Phase B may start meanwhile."""
+        for a in out:
+            assert a.shape == self.shape and a.dtype == np.float64 and a.flags.c_contiguous
+        self._ck(self._L.lbg_lb_download_moments_async(self._h, *out))
+
+    def wait_transfers(self):
+        self._ck(self._L.lbg_wait_transfers(self._h))
 
     def lb_populations(self):
         n = np.zeros((19,) + self.shape)

@@ -38,6 +38,7 @@ using namespace lbg;
 namespace {
 
 constexpr int SLOT_CAP = 4096;  // steps per batch (one host sync per batch)
+constexpr int STAGE_SLOTS = 4;     // dense staging arrays for host transfers: the four moment arrays can be in flight at once
 constexpr int F0_ARRAYS = 19 + 4;  // arrays in the f[0] allocation: 19 populations + density, jx, jy, jz
 
 thread_local std::string g_last_error;  // per thread: several slabs may be driven from threads of one process
@@ -151,7 +152,8 @@ struct lbg_handle_s {
   cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   cudaEvent_t ev_ar[2] = {nullptr, nullptr};  // lagged vacf all-reduces of Phase B
   cudaEvent_t ev_arb = nullptr;               // blocking all-reduce on the all-reduce stream
-  cudaEvent_t ev_stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // read-back pipeline (copy_own_to_host_many)
+  bool transfers_pending = false;  // an asynchronous read-back is using the staging buffer (lbg_wait_transfers)
+  cudaEvent_t ev_stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // read-back pipeline (copy_own_to_host_many)
   bool halo_pending = false;
   // peer-to-peer halos (NVLink, copy engines): neighbours' population buffers and arrival flags
   bool p2p = false;
@@ -202,6 +204,7 @@ struct lbg_handle_s {
   unsigned long long* h_l2 = nullptr;
   double* h_vacf = nullptr;
   Ctrl* h_ctrl = nullptr;
+  unsigned char* h_small = nullptr;  // scratch for small reads (read_small_async)
 
   d3q19::Consts k{};
   int grid_lb = 148, grid_mp = 148;
@@ -703,6 +706,7 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   CKB(cudaMallocHost(&h->h_l2, 2 * SLOT_CAP * sizeof(unsigned long long)));
   CKB(cudaMallocHost(&h->h_vacf, 3 * SLOT_CAP * sizeof(double)));
   CKB(cudaMallocHost(&h->h_ctrl, sizeof(Ctrl)));
+  CKB(cudaMallocHost(&h->h_small, 64 * 1024));
   CKB(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->st));
   CKB(cudaMemsetAsync(h->counts, 0, 2 * sizeof(unsigned long long), h->st));
 
@@ -865,7 +869,7 @@ int ensure_second_lattice(lbg_handle h, bool zero = true) {
 }
 
 int ensure_stage(lbg_handle h) {
-  if (!h->stage) CK(cudaMalloc(&h->stage, 3 * (size_t)h->nown * sizeof(double)));
+  if (!h->stage) CK(cudaMalloc(&h->stage, (size_t)STAGE_SLOTS * (size_t)h->nown * sizeof(double)));
   return LBG_OK;
 }
 
@@ -1101,31 +1105,64 @@ int snapshot_prev_force(lbg_handle h) {
 // The staging buffer holds three dense arrays: the scatter kernel of array i+1 (compute stream) runs while the
 // copy engine moves array i to the host (communication stream).  pull_l >= 0: src[i] is ignored and array i is
 // n(t)(., pull_l + i) rebuilt from the post-collision populations `pull_from` (launch_pull_to_dense).
+// Small device -> host reads that may run while a multi-GB read-back occupies the copy engine (a cudaMemcpy of a
+// few bytes would queue behind it for tens of ms): a one-block kernel stores the bytes into page-locked host memory.
+__global__ void to_host_kernel(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, int nbytes) {
+  for (int i = threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+
+constexpr size_t SMALL_CAP = 64 * 1024;
+
+// queue a small read into the pinned scratch at byte offset `off`; valid after the next synchronisation of h->st
+int read_small_async(lbg_handle h, size_t off, const void* dev_src, size_t bytes) {
+  if (off + bytes > SMALL_CAP) return fail(h, LBG_ERR_INVALID_ARG, "read_small: too large");
+  to_host_kernel<<<1, 256, 0, h->st>>>((const unsigned char*)dev_src, h->h_small + off, (int)bytes);
+  h->launches += 1;
+  return LBG_OK;
+}
+
+int wait_transfers(lbg_handle h) {
+  if (h->transfers_pending) {
+    CK(cudaStreamSynchronize(h->st_ar));
+    h->transfers_pending = false;
+  }
+  return LBG_OK;
+}
+
+// async: return once everything is enqueued; the host arrays are valid after lbg_wait_transfers.  The copies run on
+// their own stream (not the halo stream: a multi-GB read-back must not sit in front of the next halo planes).
 int copy_own_to_host_many(lbg_handle h, double* const* dst, const double* const* src, int count,
-                          const double* pull_from = nullptr) {
+                          const double* pull_from = nullptr, bool async = false) {
+  RET(wait_transfers(h));
   RET(ensure_stage(h));
-  for (int e = 0; e < 6; ++e)
+  for (int e = 0; e < 2 * STAGE_SLOTS; ++e)
     if (!h->ev_stage[e]) CK(cudaEventCreateWithFlags(&h->ev_stage[e], cudaEventDisableTiming));
   int issued = 0;
   for (int i = 0; i < count; ++i) {
     if (!dst[i]) continue;
-    const int slot = issued % 3;
+    const int slot = issued % STAGE_SLOTS;
     double* stg = h->stage + (size_t)slot * h->nown;
-    if (issued >= 3) CK(cudaStreamWaitEvent(h->st, h->ev_stage[3 + slot], 0));  // the slot's previous copy is done
+    if (issued >= STAGE_SLOTS) CK(cudaStreamWaitEvent(h->st, h->ev_stage[STAGE_SLOTS + slot], 0));  // the slot's previous copy is done
     if (pull_from) h->launches += launch_pull_to_dense(h->geo, pull_from, i, stg, h->st);
     else h->launches += launch_scatter_to_dense(h->geo, src[i], stg, h->st);
     CK(cudaEventRecord(h->ev_stage[slot], h->st));
-    CK(cudaStreamWaitEvent(h->st_comm, h->ev_stage[slot], 0));
-    CK(cudaMemcpyAsync(dst[i], stg, (size_t)h->nown * sizeof(double), cudaMemcpyDeviceToHost, h->st_comm));
-    CK(cudaEventRecord(h->ev_stage[3 + slot], h->st_comm));
+    CK(cudaStreamWaitEvent(h->st_ar, h->ev_stage[slot], 0));
+    CK(cudaMemcpyAsync(dst[i], stg, (size_t)h->nown * sizeof(double), cudaMemcpyDeviceToHost, h->st_ar));
+    CK(cudaEventRecord(h->ev_stage[STAGE_SLOTS + slot], h->st_ar));
     ++issued;
   }
-  CK(cudaStreamSynchronize(h->st_comm));
+  if (async) {
+    h->transfers_pending = issued > 0;
+    return LBG_OK;
+  }
+  CK(cudaStreamSynchronize(h->st_ar));
   CK(cudaStreamSynchronize(h->st));
   return LBG_OK;
 }
 
 int copy_own_to_device(lbg_handle h, double* arr, const double* src) {
+  RET(wait_transfers(h));
   RET(ensure_stage(h));
   CK(cudaMemcpyAsync(h->stage, src, (size_t)h->nown * sizeof(double), cudaMemcpyHostToDevice, h->st));
   h->launches += launch_gather_from_dense(h->geo, h->stage, arr, h->st);
@@ -1229,6 +1266,7 @@ int lbg_get_nature(lbg_handle h, int8_t* out) {
 int lbg_destroy(lbg_handle h) {
   if (!h) return LBG_OK;
   cudaSetDevice(h->device);
+  h->transfers_pending = false;
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->st_comm) cudaStreamSynchronize(h->st_comm);
   if (h->st_ar) cudaStreamSynchronize(h->st_ar);
@@ -1265,12 +1303,13 @@ int lbg_destroy(lbg_handle h) {
   cudaFreeHost(h->h_l2);
   cudaFreeHost(h->h_vacf);
   cudaFreeHost(h->h_ctrl);
+  cudaFreeHost(h->h_small);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   if (h->ev_halo) cudaEventDestroy(h->ev_halo);
   if (h->ev_arb) cudaEventDestroy(h->ev_arb);
   if (h->ev_ar[0]) cudaEventDestroy(h->ev_ar[0]);
   if (h->ev_ar[1]) cudaEventDestroy(h->ev_ar[1]);
-  for (int e = 0; e < 6; ++e)
+  for (int e = 0; e < 8; ++e)
     if (h->ev_stage[e]) cudaEventDestroy(h->ev_stage[e]);
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
@@ -1838,7 +1877,7 @@ int lbg_lb_step(lbg_handle h, double tau, int nsteps, int check_every, double ta
   return LBG_OK;
 }
 
-int lbg_lb_download_moments(lbg_handle h, double* rho, double* jx, double* jy, double* jz) {
+static int download_moments(lbg_handle h, double* rho, double* jx, double* jy, double* jz, bool async) {
   if (!h) return LBG_ERR_INVALID_ARG;
   CK(cudaSetDevice(h->device));
   RET(refresh_moments(h, nullptr));
@@ -1846,7 +1885,21 @@ int lbg_lb_download_moments(lbg_handle h, double* rho, double* jx, double* jy, d
   const double* src[4];
   for (int c = 0; c < 4; ++c) src[c] = h->mom + (long long)c * h->geo.nfa;
   RET(wait_halo(h));
-  return copy_own_to_host_many(h, dst, src, 4);
+  return copy_own_to_host_many(h, dst, src, 4, nullptr, async);
+}
+
+int lbg_lb_download_moments(lbg_handle h, double* rho, double* jx, double* jy, double* jz) {
+  return download_moments(h, rho, jx, jy, jz, false);
+}
+
+int lbg_lb_download_moments_async(lbg_handle h, double* rho, double* jx, double* jy, double* jz) {
+  return download_moments(h, rho, jx, jy, jz, true);
+}
+
+int lbg_wait_transfers(lbg_handle h) {
+  if (!h) return LBG_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  return wait_transfers(h);
 }
 
 int lbg_lb_download_populations(lbg_handle h, double* n) {
@@ -1984,8 +2037,9 @@ static int mp_init_impl(lbg_handle h, double Db, double ka, double kd, const dou
     CK(cudaMemcpyAsync(h->counts, c2, sizeof(c2), cudaMemcpyHostToDevice, h->st));
     RET(allreduce(h, h->counts, 2, AR_U64_SUM));
     RET(wait_halo(h));
-    CK(cudaMemcpyAsync(c2, h->counts, sizeof(c2), cudaMemcpyDeviceToHost, h->st));
+    RET(read_small_async(h, 0, h->counts, sizeof(c2)));
     CK(cudaStreamSynchronize(h->st));
+    std::memcpy(c2, h->h_small, sizeof(c2));
     nf = (long long)c2[0];
     nif = (long long)c2[1];
   }
@@ -2022,8 +2076,9 @@ static int mp_init_impl(lbg_handle h, double Db, double ka, double kd, const dou
     CK(cudaMemsetAsync(h->counts, 0, sizeof(unsigned long long), h->st));
     h->launches += launch_scan_ranks(h->awords, ngroups, h->counts, h->st);
     unsigned long long slots = 0;
-    CK(cudaMemcpyAsync(&slots, h->counts, sizeof(slots), cudaMemcpyDeviceToHost, h->st));
+    RET(read_small_async(h, 0, h->counts, sizeof(slots)));
     CK(cudaStreamSynchronize(h->st));
+    std::memcpy(&slots, h->h_small, sizeof(slots));
     h->a_stride = ((long long)slots + 31) / 32 * 32;
     if (h->a_stride > g.nfa) return fail(h, LBG_ERR_STATE, "adsorbed storage does not fit");  // cannot happen: slots <= nf + 3 nf / 32... guard anyway
   }
@@ -2050,10 +2105,12 @@ static int mp_init_impl(lbg_handle h, double Db, double ka, double kd, const dou
   h->launches += launch_mp_init(a, grid, h->st);
   std::vector<double> part((size_t)grid * 3);
   int bad = 0;
-  CK(cudaMemcpyAsync(part.data(), h->partial, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  CK(cudaMemcpyAsync(&bad, h->mp_err, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  RET(read_small_async(h, 0, h->partial, part.size() * sizeof(double)));
+  RET(read_small_async(h, SMALL_CAP - 64, h->mp_err, sizeof(int)));
   CK(cudaStreamSynchronize(h->st));
   CK(cudaGetLastError());
+  std::memcpy(part.data(), h->h_small, part.size() * sizeof(double));
+  std::memcpy(&bad, h->h_small + SMALL_CAP - 64, sizeof(int));
   double v0[3] = {0, 0, 0};
   for (int b = 0; b < grid; ++b)
     for (int d = 0; d < 3; ++d) v0[d] += part[(size_t)b * 3 + d];
@@ -2061,13 +2118,15 @@ static int mp_init_impl(lbg_handle h, double Db, double ka, double kd, const dou
     CK(cudaMemcpyAsync(h->vacf_slots, v0, sizeof(v0), cudaMemcpyHostToDevice, h->st));
     RET(allreduce(h, h->vacf_slots, 3, AR_F64_SUM));
     RET(wait_halo(h));
-    CK(cudaMemcpyAsync(v0, h->vacf_slots, sizeof(v0), cudaMemcpyDeviceToHost, h->st));
+    RET(read_small_async(h, 0, h->vacf_slots, sizeof(v0)));
     unsigned long long badsum = bad ? 1ull : 0ull;
     CK(cudaMemcpyAsync(h->counts, &badsum, sizeof(badsum), cudaMemcpyHostToDevice, h->st));
     RET(allreduce(h, h->counts, 1, AR_U64_MAX));
     RET(wait_halo(h));
-    CK(cudaMemcpyAsync(&badsum, h->counts, sizeof(badsum), cudaMemcpyDeviceToHost, h->st));
+    RET(read_small_async(h, 64, h->counts, sizeof(badsum)));
     CK(cudaStreamSynchronize(h->st));
+    std::memcpy(v0, h->h_small, sizeof(v0));
+    std::memcpy(&badsum, h->h_small + 64, sizeof(badsum));
     bad = badsum ? 1 : 0;
     // P(now) halo planes for the first step
     const int all3[3] = {0, 1, 2};
@@ -2231,6 +2290,7 @@ int lbg_mp_download(lbg_handle h, double* P, double* Pads) {
   if (h->phase != PH_MP) return fail(h, LBG_ERR_STATE, "lbg_mp_download needs lbg_mp_init first");
   CK(cudaSetDevice(h->device));
   RET(wait_halo(h));
+  RET(wait_transfers(h));
   RET(ensure_stage(h));
   if (P) {
     h->launches += launch_scatter3_to_dense_aos(h->geo, h->P[h->pc], h->stage, h->st);

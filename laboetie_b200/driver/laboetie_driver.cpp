@@ -277,17 +277,17 @@ int main(int argc, char** argv) {
     // never run past the step before the next profile dump
     const long limit = (t + 1 == next_write) ? print_files_frequency : next_write - 1 - t;
     chunk = std::min(chunk, std::max(limit, 1L));
+    if (tmf) {  // equilibration.f90:259-261 writes `t, SUM(jx), ...` before jx is updated in step t: the flux of step t-1
+      double tf[3];
+      ck(lbg_lb_total_flux(h, tf), h, "equilibration (total flux)");
+      std::fprintf(tmf, "%12ld %15.7E %15.7E %15.7E\n", t + 1, tf[0], tf[1], tf[2]);
+    }
     int done = 0, conv = 0;
     ck(lbg_lb_step(h, tau, (int)chunk, 1, target_error, hist.data(), &done, &conv), h, "equilibration");
     for (int i = 0; i < done; ++i) {
       ++t;
       std::fprintf(l2f, "%12ld %24.16E\n", t, hist[i]);
       if (!quiet && t % print_frequency == 0) std::printf(" %11ld %14.7E (target %10.3E )\n", t, hist[i], target_error);
-    }
-    if (tmf) {
-      double tf[3];
-      ck(lbg_lb_total_flux(h, tf), h, "equilibration (total flux)");
-      std::fprintf(tmf, "%12ld %15.7E %15.7E %15.7E\n", t, tf[0], tf[1], tf[2]);
     }
     if (!conv) continue;
     if (!without_fext) {  // :377-386

@@ -745,6 +745,34 @@ def test_benchmark_shaped_lattices_against_oracle(name, mk, f, want_nbt, in_plac
         assert (np.abs(v - ref_v) <= tol * np.abs(mp.vacf0).max()).all()
 
 
+def test_asynchronous_moments_read_back():
+    """lbg_lb_download_moments_async: Phase B runs while density / momentum cross PCIe; same arrays as the blocking call."""
+    lb = _gpu()
+    nat = random_nature(21, 9, 8, 0.3, 61)
+    f = [1e-4, 0, 2e-4]
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_init(1.0)
+        sim.lb_set_force_uniform(f)
+        sim.lb_step(7, tau=0.9, check_every=1, target_error=-1.0)
+        ref = sim.lb_moments()
+        out = [np.full(nat.shape, np.nan) for _ in range(4)]
+        sim.lb_moments_async(out)
+        v0 = sim.mp_init(0.01, 0.1, 0.01, f)
+        done, _, v = sim.mp_step(5)
+        P, A = sim.mp_download()          # shares the staging buffer: must wait for the queued read-back itself
+        sim.wait_transfers()
+        for a, b in zip(out, ref):
+            assert np.array_equal(a, b)
+    with lb.LaboetieGPU(nat) as sim:     # same Phase B without the overlapped read-back
+        sim.lb_init(1.0)
+        sim.lb_set_force_uniform(f)
+        sim.lb_step(7, tau=0.9, check_every=1, target_error=-1.0)
+        assert np.array_equal(sim.mp_init(0.01, 0.1, 0.01, f), v0)
+        _, _, v2 = sim.mp_step(5)
+        P2, A2 = sim.mp_download()
+        assert np.array_equal(v, v2) and np.array_equal(P, P2) and np.array_equal(A, A2)
+
+
 def test_shape_checks_in_the_python_binding():
     lb = _gpu()
     nat = random_nature(6, 5, 4, 0.2, 3)
