@@ -11,10 +11,12 @@
 // of the adsorbed quantity (the reference drops its populations there too, drop_tracers.f90:85).
 // The driver's dense (i,j,k) arrays are scattered / gathered at the phase boundaries.
 //
-// Multi-GPU: the slab ring exchanges, per step, the 5 populations leaving each z-face.  A plane's
-// fluid nodes are one contiguous fid range, so ncclSend/ncclRecv work straight on the boundary and
-// halo ranges -- no packing -- overlapped with the interior planes' kernel; scalars go through
-// ncclAllReduce.  NCCL is loaded with dlopen only when lbg_comm_init is called.
+// Multi-GPU: the slab ring exchanges, per step, the 5 populations leaving each z-face.  A plane's fluid nodes are one
+// contiguous fid range, so a face is 5 contiguous runs that the copy engines push over NVLink into the
+// neighbour's small IPC-mapped receive buffer (unpacked into the halo ranges by halo_unpack_kernel), overlapped
+// with the interior planes' kernel; scalars are all-reduced by a one-warp kernel over the peers' mailboxes.
+// NCCL (loaded with dlopen only when lbg_comm_init is called) bootstraps the handle exchange and is the fallback
+// transport (LBG_HALO=nccl).
 #include <dlfcn.h>
 #include <nccl.h>
 #include <time.h>
