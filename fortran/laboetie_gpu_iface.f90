@@ -15,7 +15,7 @@ module laboetie_gpu
   public :: lbg_get_interfacial, lbg_get_counts
   public :: lbg_lb_set_in_place, lbg_lb_init, lbg_lb_upload, lbg_lb_set_force_uniform, lbg_lb_set_force_field, lbg_lb_step, lbg_lb_time
   public :: lbg_lb_download_moments, lbg_lb_download_populations, lbg_lb_profiles, lbg_lb_total_flux, lbg_lb_probe
-  public :: lbg_lb_download_moments_async, lbg_wait_transfers, lbg_get_info
+  public :: lbg_lb_download_moments_async, lbg_wait_transfers, lbg_get_info, lbg_lb_slice
   public :: lbg_mp_init, lbg_mp_init_from_moments, lbg_mp_step, lbg_mp_download, lbg_sync, lbg_status_message
 
   integer(c_int), parameter, public :: LBG_OK = 0
@@ -151,6 +151,13 @@ module laboetie_gpu
       import :: c_ptr, c_int, c_double
       type(c_ptr), value :: h
       real(c_double), intent(out) :: out(3)
+    end function
+    ! one plane of density / momentum density (equilibration.f90:526-548); axis 0: x = index -> (ly, nzl), ...
+    integer(c_int) function lbg_lb_slice(h, axis, index, rho, jx, jy, jz) bind(C, name="lbg_lb_slice")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: axis, index
+      real(c_double), intent(out) :: rho(*), jx(*), jy(*), jz(*)
     end function
     integer(c_int) function lbg_lb_probe(h, i, j, k, out) bind(C, name="lbg_lb_probe")
       import :: c_ptr, c_int, c_double

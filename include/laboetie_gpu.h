@@ -148,6 +148,11 @@ int lbg_lb_download_populations(lbg_handle h, double* n);
 int lbg_lb_profiles(lbg_handle h, int axis, int raw, double* out);
 /* equilibration.f90:260: SUM(jx), SUM(jy), SUM(jz) (own planes) */
 int lbg_lb_total_flux(lbg_handle h, double out[3]);
+/* equilibration.f90:526-548: one plane of density / momentum density for the 2-D field files
+ * (mass-flux_field_2d_at_x.eq.1.dat, f_ext-field.dat, vel-field_central.dat) without reading the whole lattice back.
+ * axis 0: x = index, arrays (ly, nzl) with j fastest; axis 1: y = index, (lx, nzl), i fastest; axis 2: own plane
+ * k = index, (lx, ly), i fastest.  0-based index; any of the four outputs may be NULL; 0 on solid nodes. */
+int lbg_lb_slice(lbg_handle h, int axis, int index, double* rho, double* jx, double* jy, double* jz);
 /* equilibration.f90:187: jx,jy,jz,density at one node (0-based, own-plane k) */
 int lbg_lb_probe(lbg_handle h, int i, int j, int k, double out[4]);
 

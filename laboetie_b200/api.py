@@ -27,7 +27,7 @@ SYMBOLS = [
     "lbg_create", "lbg_create_slab", "lbg_create_geometry", "lbg_get_nature", "lbg_destroy", "lbg_comm_unique_id", "lbg_comm_init", "lbg_get_interfacial",
     "lbg_get_counts", "lbg_lb_set_in_place", "lbg_lb_init", "lbg_lb_upload", "lbg_lb_set_force_uniform", "lbg_lb_set_force_field",
     "lbg_lb_step", "lbg_lb_time", "lbg_lb_download_moments", "lbg_lb_download_moments_async", "lbg_wait_transfers", "lbg_lb_download_populations", "lbg_lb_profiles",
-    "lbg_lb_total_flux", "lbg_lb_probe", "lbg_mp_init", "lbg_mp_init_from_moments", "lbg_mp_step", "lbg_mp_download", "lbg_timer_start",
+    "lbg_lb_total_flux", "lbg_lb_slice", "lbg_lb_probe", "lbg_mp_init", "lbg_mp_init_from_moments", "lbg_mp_step", "lbg_mp_download", "lbg_timer_start",
     "lbg_timer_stop", "lbg_launch_count", "lbg_get_info", "lbg_sync",
 ]
 
@@ -85,6 +85,7 @@ def load_library():
     L.lbg_lb_download_populations.argtypes = [P, f64]
     L.lbg_lb_profiles.argtypes = [P, I, I, f64]
     L.lbg_lb_total_flux.argtypes = [P, f64]
+    L.lbg_lb_slice.argtypes = [P, I, I, P, P, P, P]
     L.lbg_lb_probe.argtypes = [P, I, I, I, f64]
     L.lbg_mp_init.argtypes = [P, D, D, D, C.POINTER(D * 3), f64]
     L.lbg_mp_init_from_moments.argtypes = [P, f64, f64, f64, f64, D, D, D, C.POINTER(D * 3), f64]
@@ -292,6 +293,13 @@ class LaboetieGPU:
     def lb_total_flux(self):
         out = np.zeros(3)
         self._ck(self._L.lbg_lb_total_flux(self._h, out))
+        return out
+
+    def lb_slice(self, axis, index):
+        """rho, jx, jy, jz on one plane (axis 0: x = index -> (nzl, ly); 1: y = index -> (nzl, lx); 2: z = index -> (ly, lx))."""
+        shape = [(self.nzl, self.ly), (self.nzl, self.lx), (self.ly, self.lx)][axis]
+        out = [np.zeros(shape) for _ in range(4)]
+        self._ck(self._L.lbg_lb_slice(self._h, axis, index, *[a.ctypes.data_as(C.c_void_p) for a in out]))
         return out
 
     def lb_probe(self, i, j, k):

@@ -1981,6 +1981,24 @@ int lbg_lb_total_flux(lbg_handle h, double out[3]) {
   return LBG_OK;
 }
 
+int lbg_lb_slice(lbg_handle h, int axis, int index, double* rho, double* jx, double* jy, double* jz) {
+  if (!h || axis < 0 || axis > 2 || index < 0) return LBG_ERR_INVALID_ARG;
+  const int extent = axis == 0 ? h->geo.lx : (axis == 1 ? h->geo.ly : h->geo.nzl);
+  if (index >= extent) return LBG_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  RET(refresh_moments(h, nullptr));
+  RET(wait_transfers(h));
+  RET(ensure_stage(h));   // a plane is never larger than the staging buffer (lx, ly, nzl >= 1)
+  const size_t n = (size_t)(axis == 0 ? h->geo.ly : h->geo.lx) * (size_t)(axis == 2 ? h->geo.ly : h->geo.nzl);
+  if (4 * n > (size_t)STAGE_SLOTS * (size_t)h->nown) return fail(h, LBG_ERR_INVALID_ARG, "lbg_lb_slice: plane larger than the lattice");
+  h->launches += launch_slice(h->geo, h->mom, axis, index, h->stage, h->st);
+  double* dst[4] = {rho, jx, jy, jz};
+  for (int c = 0; c < 4; ++c)
+    if (dst[c]) CK(cudaMemcpyAsync(dst[c], h->stage + (size_t)c * n, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return LBG_OK;
+}
+
 int lbg_lb_probe(lbg_handle h, int i, int j, int k, double out[4]) {
   if (!h || !out || i < 0 || j < 0 || k < 0 || i >= h->geo.lx || j >= h->geo.ly || k >= h->geo.nzl) return LBG_ERR_INVALID_ARG;
   CK(cudaSetDevice(h->device));

@@ -190,6 +190,26 @@ __global__ void __launch_bounds__(BLOCK) pull_to_dense_kernel(Geo geo, const dou
   }
 }
 
+// one plane of the moments (equilibration.f90:526-548: the 2-D field outputs): axis 0 -> x = index, out(j,k);
+// axis 1 -> y = index, out(i,k); axis 2 -> own plane k = index, out(i,j); first index fastest, 0 on solid nodes.
+__global__ void __launch_bounds__(BLOCK) slice_kernel(Geo geo, const double* __restrict__ mom, int axis, int index,
+                                                      double* __restrict__ out, int ncomp) {
+  const int n1 = axis == 0 ? geo.ly : geo.lx;
+  const int n2 = axis == 2 ? geo.ly : geo.nzl;
+  const long long n = (long long)n1 * n2;
+  for (long long q = (long long)blockIdx.x * BLOCK + threadIdx.x; q < n; q += (long long)gridDim.x * BLOCK) {
+    const int b = (int)(q / n1), a = (int)(q - (long long)b * n1);
+    int i, j, k;
+    if (axis == 0) { i = index; j = a; k = b; }
+    else if (axis == 1) { i = a; j = index; k = b; }
+    else { i = a; j = b; k = index; }
+    const long long g = (long long)i + (long long)geo.lx * j + (long long)geo.plane * (k + 1);
+    int fid;
+    const bool fl = lookup(geo, (int)g, fid);
+    for (int c = 0; c < ncomp; ++c) out[(long long)c * n + q] = fl ? mom[(long long)c * geo.nfa + fid] : 0.0;
+  }
+}
+
 // three SoA arrays -> the reference's AoS (x:z,i,j,k) over the own planes
 __global__ void __launch_bounds__(BLOCK) scatter3_aos_kernel(Geo geo, const double* __restrict__ soa,
                                                              double* __restrict__ aos) {
@@ -351,6 +371,12 @@ int launch_scatter_to_dense(const Geo& g, const double* arr, double* dense_own, 
 
 int launch_pull_to_dense(const Geo& g, const double* fin, int l, double* dense_own, cudaStream_t st) {
   pull_to_dense_kernel<<<big_grid((long long)g.plane * g.nzl), BLOCK, 0, st>>>(g, fin, l, dense_own);
+  return 1;
+}
+
+int launch_slice(const Geo& g, const double* mom, int axis, int index, double* out4, cudaStream_t st) {
+  const long long n = (long long)(axis == 0 ? g.ly : g.lx) * (axis == 2 ? g.ly : g.nzl);
+  slice_kernel<<<big_grid(n), BLOCK, 0, st>>>(g, mom, axis, index, out4, 4);
   return 1;
 }
 

@@ -252,6 +252,8 @@ int launch_dense_interfacial(const Geo& g, int8_t* out_own, cudaStream_t st);
 // dense <-> compact transfers over own planes (dense index relative to the first own plane)
 int launch_scatter_to_dense(const Geo& g, const double* arr, double* dense_own, cudaStream_t st);
 int launch_gather_from_dense(const Geo& g, const double* dense_own, double* arr, cudaStream_t st);
+// one plane of rho, jx, jy, jz (4 arrays of the plane's size in out4), see slice_kernel
+int launch_slice(const Geo& g, const double* mom, int axis, int index, double* out4, cudaStream_t st);
 // n(t)(., l) pulled from the post-collision populations fin into the dense own-plane order
 int launch_pull_to_dense(const Geo& g, const double* fin, int l, double* dense_own, cudaStream_t st);
 int launch_scatter3_to_dense_aos(const Geo& g, const double* soa3, double* dense_aos_own, cudaStream_t st);

@@ -745,6 +745,24 @@ def test_benchmark_shaped_lattices_against_oracle(name, mk, f, want_nbt, in_plac
         assert (np.abs(v - ref_v) <= tol * np.abs(mp.vacf0).max()).all()
 
 
+def test_plane_slices_of_the_moments():
+    """lbg_lb_slice (the 2-D field outputs of equilibration.f90:526-548) equals the same plane of the full read-back."""
+    lb = _gpu()
+    nat = random_nature(13, 7, 9, 0.3, 71)
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_init(1.0)
+        sim.lb_set_force_uniform([1e-4, -1e-4, 2e-4])
+        sim.lb_step(6, tau=0.9, check_every=1, target_error=-1.0)
+        full = sim.lb_moments()
+        for axis, idx in ((0, 0), (0, 12), (1, 3), (2, 8), (2, 0)):
+            got = sim.lb_slice(axis, idx)
+            for a, b in zip(got, full):
+                ref = b[:, :, idx] if axis == 0 else (b[:, idx, :] if axis == 1 else b[idx])
+                assert np.array_equal(a, ref)
+        with pytest.raises(lb.LbgError):
+            sim.lb_slice(0, 13)
+
+
 def test_asynchronous_moments_read_back():
     """lbg_lb_download_moments_async: Phase B runs while density / momentum cross PCIe; same arrays as the blocking call."""
     lb = _gpu()
