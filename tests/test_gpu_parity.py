@@ -552,6 +552,63 @@ def test_full_size_config3_properties():
         assert (v0 > 0).all() and (np.abs(v[-1]) < v0).all()
 
 
+def test_full_size_config5_properties(monkeypatch):
+    """BASELINE config 5 at the size bench.py measures (1024x1024x128 overlapping-sphere porous medium, 80 M fluid
+    nodes), on the code paths the library picks there by itself (dynamic tile schedule, strip order, neighbour
+    table, compact adsorbed storage): size-independent properties, and agreement bit for bit between independent
+    kernels -- two-lattice vs in-place Phase A, neighbour table vs rank lookups in Phase B."""
+    lb = _gpu()
+    from laboetie_b200 import synthetic as S
+    for v in ("LBG_MP_NBT", "LBG_LB_MINB", "LBG_LB_PIPE", "LBG_LB_TPC", "LBG_LB_STRIP_ROWS", "LBG_MP_STRIP_ROWS"):
+        monkeypatch.delenv(v, raising=False)
+    builder, lx, ly, lz, f, _ = S.WORKLOADS["cfg5w"]
+    nat = builder(lx, ly, lz)
+    fluid = nat == 0
+    nf = int(fluid.sum())
+    f = [1e-5, 0.0, 2e-5]
+    steps = 7          # odd: the in-place buffer ends in its swapped layout
+    with lb.LaboetieGPU(nat) as sim:
+        assert sim.counts()[0] == nf
+        sim.lb_init(1.0)
+        d1, _, h1 = sim.lb_step(3, tau=0.9, check_every=1, target_error=-1.0)
+        sim.lb_set_force_uniform(f)
+        d2, _, h2 = sim.lb_step(steps - 3, tau=0.9, check_every=1, target_error=-1.0)
+        assert d1 + d2 == steps and sim.info("lb_variant") == 13      # plain kernel, dynamic schedule, 3 CTAs per SM
+        rho, jx, jy, jz = sim.lb_moments()
+        assert (rho[~fluid] == 0).all() and (jz[~fluid] == 0).all()
+        assert abs(rho.sum() - nf) <= 1e-12 * nf                         # mass conservation
+        assert jx.sum() > 0 and jz.sum() > 0
+        Db, ka, kd = 0.01, 0.1, 0.01
+        v0 = sim.mp_init(Db, ka, kd, f)
+        assert sim.info("mp_neighbour_table") == 1
+        P0, _ = sim.mp_download(want_ads=False)
+        tot0, scale = P0.sum(axis=(0, 1, 2)), np.abs(P0).sum()
+        del P0
+        done, _, v = sim.mp_step(5)
+        assert done == 5 and np.isfinite(v).all() and (v0 > 0).all()
+        P, A = sim.mp_download()
+        assert (P[~fluid] == 0).all() and (A[~fluid] == 0).all() and (A != 0).any()
+        assert np.allclose((P.sum(axis=(0, 1, 2)) + A.sum(axis=(0, 1, 2))), tot0, rtol=0, atol=1e-11 * scale)   # sum(P + Pads) conserved
+    # the same Phase A in place (AA kernels), the same Phase B through rank lookups
+    monkeypatch.setenv("LBG_MP_NBT", "0")
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_set_in_place(True)
+        sim.lb_init(1.0)
+        _, _, g1 = sim.lb_step(3, tau=0.9, check_every=1, target_error=-1.0)
+        sim.lb_set_force_uniform(f)
+        _, _, g2 = sim.lb_step(steps - 3, tau=0.9, check_every=1, target_error=-1.0)
+        assert np.array_equal(g1, h1) and np.array_equal(g2, h2)
+        for a, b in zip(sim.lb_moments(), (rho, jx, jy, jz)):
+            assert np.array_equal(a, b)
+        del rho, jx, jy, jz
+        w0 = sim.mp_init(Db, ka, kd, f)
+        assert sim.info("mp_neighbour_table") == 0
+        _, _, w = sim.mp_step(5)
+        P2, A2 = sim.mp_download()
+        assert np.array_equal(P2, P) and np.array_equal(A2, A)
+        assert np.allclose(w0, v0, rtol=1e-9, atol=0) and np.allclose(w, v, rtol=0, atol=1e-9 * np.abs(v0).max())
+
+
 def itf_not(nat):
     itf = O.detect_interfacial(nat)
     return ~((itf == 1) & (nat == 0))
