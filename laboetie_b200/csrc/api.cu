@@ -184,6 +184,7 @@ struct lbg_handle_s {
   std::vector<bool> peer_mail_ipc;
   unsigned long long** d_peer_mail = nullptr;   // the same on the device
   unsigned long long ar_seq = 0;                // all-reduces issued so far
+  long long spin_clocks = 40000000000LL;        // bounded spins of the peer-to-peer waits (~20 s; LBG_P2P_TIMEOUT_S)
   int comm_slot = -1;                           // entry of the process-wide communicator cache in use (-1: own comm)
   unsigned int* flags = nullptr;   // = (unsigned int*)mail
   unsigned int xseq = 0;           // exchanges issued so far
@@ -318,13 +319,13 @@ __global__ void p2p_signal_kernel(unsigned int* flag_a, unsigned int* flag_b, un
 
 // wait until both neighbours' halo data of exchange `seq` have landed; bounded spin (no GPU hang if a
 // neighbour died): on time-out the control block's stop flag is raised and *err set
-__global__ void p2p_wait_kernel(const unsigned int* flags, unsigned int seq, Ctrl* ctrl, int* err) {
+__global__ void p2p_wait_kernel(const unsigned int* flags, unsigned int seq, Ctrl* ctrl, int* err, long long max_clocks) {
   const long long t0 = clock64();
   for (;;) {
     const unsigned int a = *(volatile const unsigned int*)&flags[0];
     const unsigned int b = *(volatile const unsigned int*)&flags[1];
     if ((int)(a - seq) >= 0 && (int)(b - seq) >= 0) break;
-    if (clock64() - t0 > 40000000000LL) {  // ~20 s
+    if (clock64() - t0 > max_clocks) {  // LBG_P2P_TIMEOUT_S, default ~20 s
       ctrl->stop = 1;
       *err = 2;
       break;
@@ -482,7 +483,7 @@ int wait_halo(lbg_handle h) {
     h->halo_pending = false;
   }
   if (h->p2p && h->xwait) {  // the neighbours' pushes of the latest exchange must have landed
-    p2p_wait_kernel<<<1, 1, 0, h->st>>>(h->flags, h->xwait, h->ctrl, h->p2p_err);
+    p2p_wait_kernel<<<1, 1, 0, h->st>>>(h->flags, h->xwait, h->ctrl, h->p2p_err, h->spin_clocks);
     h->launches += 1;
     h->xwait = 0;
   }
@@ -557,7 +558,7 @@ enum ArOp { AR_U64_MAX = 0, AR_U64_SUM = 1, AR_F64_SUM = 2 };
 
 __global__ void p2p_allreduce_kernel(unsigned long long* const* peer_mail, int nranks, int rank,
                                      unsigned long long seq, unsigned long long* buf, int n, int op, Ctrl* ctrl,
-                                     int* err) {
+                                     int* err, long long max_clocks) {
   const int par = (int)(seq & 1ull);
   for (int r = threadIdx.x; r < nranks; r += blockDim.x) {
     volatile unsigned long long* slot = peer_mail[r] + MAIL_OFF + ((size_t)par * nranks + rank) * MAIL_WORDS;
@@ -570,7 +571,7 @@ __global__ void p2p_allreduce_kernel(unsigned long long* const* peer_mail, int n
   for (int r = threadIdx.x; r < nranks; r += blockDim.x) {
     const volatile unsigned long long* slot = peer_mail[rank] + MAIL_OFF + ((size_t)par * nranks + r) * MAIL_WORDS;
     while (slot[0] < seq) {
-      if (clock64() - t0 > 40000000000LL) {  // ~20 s: a peer died; give up instead of hanging the GPU
+      if (clock64() - t0 > max_clocks) {  // a peer died; give up instead of hanging the GPU
         ctrl->stop = 1;
         *err = 3;
         break;
@@ -604,7 +605,7 @@ int allreduce(lbg_handle h, void* buf, size_t n, ArOp op) {
     if (n > MAIL_WORDS - 1) return fail(h, LBG_ERR_INVALID_ARG, "allreduce: too many words");
     ++h->ar_seq;
     p2p_allreduce_kernel<<<1, 32, 0, h->st>>>(h->d_peer_mail, h->nranks, h->rank, h->ar_seq, (unsigned long long*)buf,
-                                              (int)n, (int)op, h->ctrl, h->p2p_err);
+                                              (int)n, (int)op, h->ctrl, h->p2p_err, h->spin_clocks);
     h->launches += 1;
     return LBG_OK;
   }
@@ -1256,12 +1257,12 @@ int lbg_create_geometry(lbg_handle* out, int label, int lx, int ly, int lz_globa
 int lbg_get_nature(lbg_handle h, int8_t* out) {
   if (!h || !out) return LBG_ERR_INVALID_ARG;
   CK(cudaSetDevice(h->device));
-  int8_t* d = nullptr;
-  CK(cudaMalloc(&d, (size_t)h->nown));
+  RET(wait_transfers(h));
+  RET(ensure_stage(h));   // scratch: no allocation per call
+  int8_t* d = reinterpret_cast<int8_t*>(h->stage);
   h->launches += launch_dense_nature(h->geo, d, h->st);
   CK(cudaMemcpyAsync(out, d, (size_t)h->nown, cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
-  cudaFree(d);
   return LBG_OK;
 }
 
@@ -1373,6 +1374,10 @@ int lbg_comm_init(lbg_handle h, int nranks, int rank, const void* id) {
   tm.lap("communicator");
   h->nranks = nranks;
   h->rank = rank;
+  if (const char* e = std::getenv("LBG_P2P_TIMEOUT_S")) {
+    const double sec = std::atof(e);
+    if (sec > 0) h->spin_clocks = (long long)(sec * 2.0e9);
+  }
   // ---- peer-to-peer: map the ring neighbours' population buffers and every rank's mailbox (same node, NVLink)
   {
     struct PeerInfo {
@@ -1509,12 +1514,12 @@ int lbg_comm_init(lbg_handle h, int nranks, int rank, const void* id) {
 int lbg_get_interfacial(lbg_handle h, int8_t* out) {
   if (!h || !out) return LBG_ERR_INVALID_ARG;
   CK(cudaSetDevice(h->device));
-  int8_t* d = nullptr;
-  CK(cudaMalloc(&d, (size_t)h->nown));
+  RET(wait_transfers(h));
+  RET(ensure_stage(h));
+  int8_t* d = reinterpret_cast<int8_t*>(h->stage);
   h->launches += launch_dense_interfacial(h->geo, d, h->st);
   CK(cudaMemcpyAsync(out, d, (size_t)h->nown, cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
-  cudaFree(d);
   return LBG_OK;
 }
 
@@ -1944,8 +1949,12 @@ int lbg_lb_profiles(lbg_handle h, int axis, int raw, double* out) {
   CK(cudaSetDevice(h->device));
   RET(refresh_moments(h, nullptr));
   const int rows = axis == 0 ? h->geo.lx : (axis == 1 ? h->geo.ly : h->geo.nzl);
-  double* d = nullptr;
-  CK(cudaMalloc(&d, (size_t)rows * 5 * sizeof(double)));
+  RET(wait_transfers(h));
+  RET(ensure_stage(h));
+  // scratch in the staging buffer when it is large enough (5 values per row), else a one-off allocation
+  const bool own_alloc = (size_t)rows * 5 > (size_t)STAGE_SLOTS * (size_t)h->nown;
+  double* d = h->stage;
+  if (own_alloc) CK(cudaMalloc(&d, (size_t)rows * 5 * sizeof(double)));
   ProfileArgs a{};
   a.geo = h->geo;
   a.mom = h->mom;
@@ -1956,7 +1965,7 @@ int lbg_lb_profiles(lbg_handle h, int axis, int raw, double* out) {
   std::vector<double> tmp((size_t)rows * 5);
   CK(cudaMemcpyAsync(tmp.data(), d, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
-  cudaFree(d);
+  if (own_alloc) cudaFree(d);
   for (int p = 0; p < rows; ++p) {
     if (raw) {
       for (int c = 0; c < 5; ++c) out[(size_t)p * 5 + c] = tmp[(size_t)p * 5 + c];

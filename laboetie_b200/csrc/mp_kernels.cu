@@ -31,6 +31,41 @@ using namespace d3q19;
 
 namespace {
 
+// Streamed operands (read once per step: link probabilities, remaining fraction, u*, table words, adsorbed
+// quantity).  LBG_MP_LD selects the cache hint: 0 = ld.global.cs (evict first), 1 = ld.global.cg (L2 only),
+// 2 = L1::no_allocate (keeps L1 for the 54 gathers), 3 = L1::no_allocate + L2 evict-first policy.
+#ifndef LBG_MP_LD
+#define LBG_MP_LD 0
+#endif
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T* p) {
+#if LBG_MP_LD == 0
+  return __ldcs(p);
+#elif LBG_MP_LD == 1
+  return __ldcg(p);
+#else
+  T v;
+  if constexpr (sizeof(T) == 8) {
+    unsigned long long r;
+#if LBG_MP_LD == 2
+    asm volatile("ld.global.L1::no_allocate.b64 %0, [%1];" : "=l"(r) : "l"(p));
+#else
+    asm volatile("ld.global.L1::no_allocate.L2::evict_first.b64 %0, [%1];" : "=l"(r) : "l"(p));
+#endif
+    v = *reinterpret_cast<T*>(&r);
+  } else {
+    unsigned int r;
+#if LBG_MP_LD == 2
+    asm volatile("ld.global.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(p));
+#else
+    asm volatile("ld.global.L1::no_allocate.L2::evict_first.b32 %0, [%1];" : "=r"(r) : "l"(p));
+#endif
+    v = *reinterpret_cast<T*>(&r);
+  }
+  return v;
+#endif
+}
+
 // block-wide sums of three values in a fixed order; result valid on thread 0
 __device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double (*sh)[BLOCK / 32]) {
   a = warp_sum(a);
@@ -230,10 +265,10 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
   auto load_words = [&](long long f) {
     if (a.ads) aw_next = __ldg(a.awords + (f >> 5));
     if constexpr (NBT) {
-      w_next[0] = __ldcs(a.nbt01 + f);
-      w_next[1] = __ldcs(a.nbt01 + nfa + f);
+      w_next[0] = ld_stream(a.nbt01 + f);
+      w_next[1] = ld_stream(a.nbt01 + nfa + f);
 #pragma unroll
-      for (int r = 2; r < NW; ++r) w_next[r] = __ldcs(a.nbt27 + (long long)(r - 2) * nfa + f);
+      for (int r = 2; r < NW; ++r) w_next[r] = ld_stream(a.nbt27 + (long long)(r - 2) * nfa + f);
     } else {
       w_next[0] = __ldg(geo.gidx + f);
     }
@@ -327,16 +362,16 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
     double q[NV - 1];
     static_for<1, NV>([&](auto Lc) {
       constexpr int L = decltype(Lc)::value;
-      q[L - 1] = __ldcs(a.q + (long long)(L - 1) * nfa + fid);
+      q[L - 1] = ld_stream(a.q + (long long)(L - 1) * nfa + fid);
     });
-    const double frac = __ldcs(a.s + fid);
-    const double usx = __ldcs(a.s + nfa + fid), usy = __ldcs(a.s + 2 * nfa + fid), usz = __ldcs(a.s + 3 * nfa + fid);
+    const double frac = ld_stream(a.s + fid);
+    const double usx = ld_stream(a.s + nfa + fid), usy = ld_stream(a.s + 2 * nfa + fid), usz = ld_stream(a.s + 3 * nfa + fid);
     const double px = a.Pnow[fid], py = a.Pnow[nfa + fid], pz = a.Pnow[2 * nfa + fid];
     double sx = 0.0, sy = 0.0, sz = 0.0;
     if (adsorbing) {
-      sx = __ldcs(a.Anow + aslot);
-      sy = __ldcs(a.Anow + a.a_stride + aslot);
-      sz = __ldcs(a.Anow + 2 * a.a_stride + aslot);
+      sx = ld_stream(a.Anow + aslot);
+      sy = ld_stream(a.Anow + a.a_stride + aslot);
+      sz = ld_stream(a.Anow + 2 * a.a_stride + aslot);
     }
     double ax = 0.0, ay = 0.0, az = 0.0;  // Propagated_Quantity(:,r,next) is always 0 on entry
     static_for<1, NV>([&](auto Lc) {
