@@ -143,3 +143,39 @@ def test_slab_equilibration_exit_step():
         assert (r["t_exit"], r["t_fext"]) == (ref["t_exit"], ref["t_fext"])
         assert np.array_equal(r["l2err"], ref["l2err"])
         assert np.array_equal(r["jx"], jx_ref[r["k0"]:r["k0"] + r["nzl"]])
+
+
+def test_dead_neighbour_is_an_error_not_a_hang(monkeypatch):
+    """A rank whose neighbour never sends its halo planes gets LBG_ERR_NCCL after the bounded spin of the wait
+    kernels (LBG_P2P_TIMEOUT_S), instead of hanging the GPU."""
+    import time
+    import laboetie_b200 as lb
+    from laboetie_b200 import api, slab
+    if _ndev() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("LBG_P2P_TIMEOUT_S", "1")
+    nat = random_nature(8, 6, 10, 0.2, 5)
+    uid = api.comm_unique_id()
+    gate = threading.Event()
+
+    def rank_fn(r):
+        sim = slab.make_slab_sim(nat, r, 2, device=r, unique_id=uid)
+        try:
+            sim.lb_init(1.0)          # collective: both ranks get here
+            if r == 1:
+                gate.wait(timeout=60)   # this rank "dies": it never steps
+                return "idle"
+            t0 = time.time()
+            try:
+                sim.lb_step(3, tau=1.0, check_every=1, target_error=-1.0)
+            except lb.LbgError as e:
+                return ("error", e.status, time.time() - t0)
+            finally:
+                gate.set()
+            return ("no error", 0, time.time() - t0)
+        finally:
+            sim.close()
+
+    res = _run_ranks(2, rank_fn)
+    kind, status, dt = res[0]
+    assert kind == "error" and status == 12 and dt < 30, res[0]
