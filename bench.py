@@ -55,9 +55,11 @@ def parse():
     ap.add_argument("--check-every", type=int, default=1, help="1 = reference semantics (l2err every step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=20.0)
-    ap.add_argument("--cpu-lattice", default="auto", choices=["auto", "full", "crop"],
-                    help="--impl reference: the workload's whole single-GPU lattice (needs ~60 GB of host memory for cfg5w) or a crop")
+    ap.add_argument("--cpu-seconds", type=float, default=None,
+                    help="seconds of CPU stepping the sample is sized for (default: 20 for cpu_baseline, 150 for --impl reference)")
+    ap.add_argument("--cpu-lattice", default="sample", choices=["sample", "full"],
+                    help="--impl reference: a slab sample sized by --cpu-seconds, or the workload's whole single-GPU lattice "
+                         "(needs ~60 GB of host memory and ~43 s per step for cfg5w)")
     ap.add_argument("--no-verify", action="store_true", help="skip the parity check of the launched configuration")
     ap.add_argument("--in-place", action="store_true", help="Phase A with the AA pattern (one population buffer)")
     ap.add_argument("--also", default="cfg2,cfg3", help="extra single-GPU workloads reported under 'also' (N=1 only)")
@@ -150,19 +152,31 @@ def host_mem_available_gb():
     return 0.0
 
 
-def cpu_run(workload, seconds, steps=None, threads=None, full=False):
-    """The reference-shaped OpenMP restatement (oracle/) on the workload's own lattice (full=True) or on a
-    bounded crop of it."""
+def workload_config(args, nranks):
+    """`config` of the JSON line: what is computed.  Both arms print the same dict for the same command line (the CPU
+    arm runs it on a bounded sample, `cpu_baseline.sample` says which)."""
+    from laboetie_b200 import synthetic as S
+    builder, lx, ly, lz_per, f_ext, desc = S.WORKLOADS[args.workload]
+    lz = lz_per * nranks if args.workload in S.WEAK else lz_per
+    return {"workload": args.workload, "description": desc, "lattice": [lx, ly, lz], "parallelism": f"z-slabs x{nranks}",
+            "tau": TAU, **TRACER, "check_every": args.check_every,
+            "phase_a_layout": "in-place (AA)" if args.in_place else "two-lattice",
+            "l2": "working set >> 126 MB L2; no flush needed",
+            "step": "1 LB step + 1 MP step; K LB steps then K MP steps timed"}
+
+
+def cpu_run(workload, nplanes, steps, warmup=1, threads=None):
+    """The reference-shaped OpenMP restatement (oracle/) on a slab sample of the workload: the lattice's whole
+    x-y cross-section, `nplanes` z-planes (all of them: the whole single-GPU lattice), periodic like the lattice.
+    `warmup` untimed and `steps` timed steps of each phase."""
     from oracle import oracle as O
     from laboetie_b200 import synthetic as S
     builder, lx, ly, lz_per, f_ext, desc = S.WORKLOADS[workload]
-    if full:
-        cx, cy, cz = lx, ly, lz_per
-        nat = builder(lx, ly, lz_per)
+    nz = max(1, min(int(nplanes), lz_per))
+    if builder in (S.bcc,):                # the BCC cell is only defined as a cube: sample the first planes of it
+        nat = np.ascontiguousarray(builder(lx, ly, lz_per)[:nz])
     else:
-        cx, cy, cz = min(lx, 256), min(ly, 256), min(lz_per, 32)
-        nat = builder(lx, ly, lz_per, k0=0, nz=cz)[:, :cy, :cx].copy() if workload != "cfg3" else builder(64, 64, 64)[:32]
-    nat = np.ascontiguousarray(nat)
+        nat = np.ascontiguousarray(builder(lx, ly, lz_per, k0=0, nz=nz))
     if nat.all():
         nat.flat[0] = 0
     ncores = os.cpu_count() or 1
@@ -175,31 +189,42 @@ def cpu_run(workload, seconds, steps=None, threads=None, full=False):
     st = O.LBState(nat, 1.0, TAU)
     st.set_force_uniform(f_ext)
     n = nat.size
-    if not full:
-        st.step()  # warm-up (page faults); at full size one step is ~40 s and the run is kept to a single one
-    t0 = time.perf_counter()
-    k = 0
-    while True:
+    for _ in range(warmup):
         st.step()
-        k += 1
-        if (steps and k >= steps) or (not steps and time.perf_counter() - t0 > seconds / 2):
-            break
-    t_lb = (time.perf_counter() - t0) / k
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st.step()
+    t_lb = (time.perf_counter() - t0) / steps
     rho, jx, jy, jz = st.rho, st.jx, st.jy, st.jz
     del st          # the reference frees its populations before Phase B too (drop_tracers.f90:85)
     mp = O.MPState(nat, itf, rho, jx, jy, jz, f_ext, TRACER["Db"], TRACER["ka"], TRACER["kd"])
-    if not full:
+    for _ in range(warmup):
         mp.propagate()
     t0 = time.perf_counter()
-    for _ in range(k):
+    for _ in range(steps):
         mp.propagate()
-    t_mp = (time.perf_counter() - t0) / k
+    t_mp = (time.perf_counter() - t0) / steps
     mlups = n / (t_lb + t_mp) / 1e6
+    whole = nz == lz_per
     return dict(value=mlups, unit="MLUPS", cores=threads or ncores, kind="port",
-                sample=f"{cx}x{cy}x{nat.shape[0]} {'(the whole lattice)' if full else 'crop'} of {workload}, {k} LB + {k} MP steps, "
-                       f"oracle/ C++/OpenMP restatement (no Fortran compiler: reference binary unavailable)",
-                lb_mlups=n / t_lb / 1e6, mp_mlups=n / t_mp / 1e6, steps=k, lattice=[cx, cy, int(nat.shape[0])],
-                full=bool(full)), (t_lb + t_mp) * 1e3
+                sample=f"{lx}x{ly}x{nz} slab of {workload} ({'the whole single-GPU lattice' if whole else 'full x-y cross-section, ' + str(nz) + ' of ' + str(lz_per) + ' z-planes'}), "
+                       f"{warmup} + {steps} LB and {warmup} + {steps} MP steps, oracle/ C++/OpenMP restatement "
+                       f"(no Fortran compiler: reference binary unavailable)",
+                lb_mlups=n / t_lb / 1e6, mp_mlups=n / t_mp / 1e6, steps=steps, lattice=[lx, ly, nz],
+                whole=bool(whole)), (t_lb + t_mp) * 1e3
+
+
+def cpu_sample_planes(workload, budget_s, nsteps_total):
+    """How many z-planes of the workload the CPU arm can step `nsteps_total` times (LB + MP) in about `budget_s`
+    seconds on this host: a one-step probe on a thin slab gives the rate."""
+    from laboetie_b200 import synthetic as S
+    builder, lx, ly, lz_per, f_ext, desc = S.WORKLOADS[workload]
+    plane = lx * ly
+    nz0 = max(2, min(lz_per, (4 << 20) // plane))
+    probe, _ = cpu_run(workload, nz0, steps=1, warmup=0)
+    rate = probe["value"] * 1e6                       # nodes per second, LB + MP
+    nz = int(budget_s * rate / (max(nsteps_total, 1) * plane))
+    return max(min(4, lz_per), min(nz, lz_per)), probe["value"]
 
 
 def run_reference(args):
@@ -208,27 +233,24 @@ def run_reference(args):
         return
     from laboetie_b200 import synthetic as S
     builder, lx, ly, lz_per, f_ext, desc = S.WORKLOADS[args.workload]
-    # The product arm's own lattice (one GPU's share of the weak-scaling workload) when the host can hold the
-    # reference's arrays for it (~0.45 KB per node at peak: populations, per-thread streaming copies, moments),
-    # else a crop.  One step of the full cfg5w lattice is ~40 s on 16 cores, so a single LB + MP step is timed
-    # there, without a warm-up step, and `steps` / `warmup` say so.
-    need_gb = 450.0 * lx * ly * lz_per / 2 ** 30
-    full = (args.cpu_lattice == "full") or (args.cpu_lattice == "auto" and host_mem_available_gb() > need_gb + 8)
-    if full:
-        res, ms = cpu_run(args.workload, args.cpu_seconds, steps=1, full=True)
-        warm = 0
+    K, W = max(args.steps, 1), max(args.warmup, 0)
+    # K timed and W warm-up steps, as asked, each on a bounded sample: the whole x-y cross-section and as many
+    # z-planes as fit --cpu-seconds of stepping (the whole single-GPU lattice with --cpu-lattice full: ~43 s per step
+    # for cfg5w on 16 cores and ~60 GB of host memory, same MLUPS -- profiles/bench_ref_r5l.json)
+    if args.cpu_lattice == "full":
+        nz, probe = lz_per, None
     else:
-        res, ms = cpu_run(args.workload, args.cpu_seconds, steps=max(1, min(args.steps, 4)))
-        warm = 1
-    # the reference's README recommends 4 OpenMP threads (README.md:94): reported beside the all-cores figure (crop)
-    res4, _ = cpu_run(args.workload, args.cpu_seconds, steps=1, threads=4)
+        nz, probe = cpu_sample_planes(args.workload, args.cpu_seconds, K + W)
+    res, ms = cpu_run(args.workload, nz, steps=K, warmup=W)
+    # the reference's README recommends 4 OpenMP threads (README.md:94): reported beside the all-cores figure
+    res4, _ = cpu_run(args.workload, max(2, min(lz_per, (4 << 20) // (lx * ly))), steps=1, warmup=0, threads=4)
     line = {"metric": "MLUPS (fp64 D3Q19 collide-stream + moment propagation)", "value": res["value"], "unit": "MLUPS",
-            "impl": "reference", "n_gpus": args.gpus, "steps": res["steps"], "requested_steps": args.steps, "warmup": warm,
-            "ms_per_step": ms,
+            "impl": "reference", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms,
             "cpu_4_threads": {"value": res4["value"], "unit": "MLUPS", "cores": res4["cores"], "sample": res4["sample"]},
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "lattice": res["lattice"],
-                       "whole_lattice_of_the_gpu_arm_at_n1": res["full"], "tau": TAU, **TRACER, "check_every": 1},
+            "higher_is_better": True, "scaling": "weak" if args.workload in S.WEAK else "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, args.gpus),
+            "sample_lattice": res["lattice"], "sample_is_whole_single_gpu_lattice": res["whole"],
+            "ms_per_step_is_for": "one LB + one MP step of the sample lattice",
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "lb_mlups": res["lb_mlups"], "mp_mlups": res["mp_mlups"]}
@@ -499,11 +521,8 @@ def run_ours(args):
         "metric": "MLUPS (fp64 D3Q19 collide-stream + moment propagation)", "value": value, "unit": "MLUPS",
         "n_gpus": nranks, "steps": K, "warmup": W, "ms_per_step": (t_lb + t_mp) / K, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "lattice": [lx, ly, lz], "parallelism": f"z-slabs x{nranks}",
-                   "fluid_fraction": nf_tot / n_total, "interfacial_fluid_fraction": nif_tot / n_total, "tau": TAU, **TRACER,
-                   "check_every": ce, "phase_a_layout": "in-place (AA)" if args.in_place else "two-lattice",
-                   "l2": "working set >> 126 MB L2; no flush needed",
-                   "step": "1 LB step + 1 MP step; K LB steps then K MP steps timed"},
+        "config": workload_config(args, nranks),
+        "lattice_stats": {"fluid_fraction": nf_tot / n_total, "interfacial_fluid_fraction": nif_tot / n_total},
         "lb": {"mlups": n_total * K / (t_lb * 1e-3) / 1e6, "mflups": nf_tot * K / (t_lb * 1e-3) / 1e6, "ms_per_step": t_lb / K},
         "mp": {"mlups": n_total * K / (t_mp * 1e-3) / 1e6, "mflups": nf_tot * K / (t_mp * 1e-3) / 1e6, "ms_per_step": t_mp / K},
         "roofline": {"bound": "hbm", "kernel": "lb_step_kernel (pull stream + moments + collide)", "achieved": lb_gbs,
@@ -522,7 +541,8 @@ def run_ours(args):
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu_baseline:
-        res, _ = cpu_run(args.workload, args.cpu_seconds)
+        nzc, _ = cpu_sample_planes(args.workload, args.cpu_seconds, 4 + 1)
+        res, _ = cpu_run(args.workload, nzc, steps=4, warmup=1)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
     # ncu-derived DRAM traffic per launch of the two step kernels (profiles/traffic_<workload>.json, written by
     # tools/ncu_traffic.py from one `ncu --set full` capture): reported only for N=1 and only if the file was
@@ -544,6 +564,8 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse()
+    if a.cpu_seconds is None:
+        a.cpu_seconds = 150.0 if a.impl == "reference" else 20.0
     if a.impl == "reference":
         run_reference(a)
     else:

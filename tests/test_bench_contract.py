@@ -17,29 +17,43 @@ def _run(*args, timeout=600):
 
 
 def test_reference_arm_json_line():
-    out = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "cfg3", "--cpu-lattice", "crop")
+    out = _run("--impl", "reference", "--steps", "2", "--warmup", "1", "--workload", "cfg3", "--cpu-seconds", "3")
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "MLUPS" and line["higher_is_better"] is True
     assert line["metric"].startswith("MLUPS") and line["value"] > 0 and line["dtype"] == "f64"
+    assert line["steps"] == 2 and line["warmup"] == 1          # what was asked for is what was timed
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "crop" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "slab of cfg3" in cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["cpu_4_threads"]["cores"] == 4 and line["cpu_4_threads"]["value"] > 0
     assert line["vs_baseline"] is None and line["config"]["workload"] == "cfg3"
-    assert line["config"]["whole_lattice_of_the_gpu_arm_at_n1"] is False
+    assert line["sample_is_whole_single_gpu_lattice"] is False and line["sample_lattice"][:2] == [256, 256]
+    # ms_per_step is the time of one LB + one MP step of the sample
+    n = line["sample_lattice"][0] * line["sample_lattice"][1] * line["sample_lattice"][2]
+    assert abs(line["ms_per_step"] - n / line["value"] / 1e3) < 1e-6 * line["ms_per_step"]
 
 
-def test_reference_arm_whole_lattice_and_step_count():
-    """With enough host memory the reference arm runs the GPU arm's own lattice (same_config), and `steps` is the
-    number of steps it really timed, whatever --steps asked for."""
-    out = _run("--impl", "reference", "--steps", "20", "--warmup", "5", "--workload", "cfg2", "--cpu-lattice", "full")
+def test_both_arms_print_the_same_config():
+    """`--impl reference` runs "your arm's config": the dict is built by one function for both arms."""
+    import argparse
+    import bench
+    args = argparse.Namespace(workload="cfg5w", check_every=1, in_place=False)
+    c = bench.workload_config(args, 4)
+    assert c["workload"] == "cfg5w" and c["lattice"] == [1024, 1024, 512] and c["parallelism"] == "z-slabs x4"
+    assert c["phase_a_layout"] == "two-lattice" and "l2" in c and c["check_every"] == 1
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": workload_config(args, ') == 2
+
+
+def test_reference_arm_whole_lattice():
+    """--cpu-lattice full: the GPU arm's own single-GPU lattice, still K timed steps after W warm-up steps."""
+    out = _run("--impl", "reference", "--steps", "3", "--warmup", "1", "--workload", "cfg2", "--cpu-lattice", "full")
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
-    assert line["config"]["lattice"] == [64, 64, 256] and line["config"]["whole_lattice_of_the_gpu_arm_at_n1"] is True
-    assert line["steps"] == 1 and line["requested_steps"] == 20 and line["warmup"] == 0
-    assert "whole lattice" in line["cpu_baseline"]["sample"]
-    assert abs(line["ms_per_step"] - 64 * 64 * 256 / line["value"] / 1e3) < 1e-6 * line["ms_per_step"]
+    assert line["config"]["lattice"] == [64, 64, 256] and line["sample_lattice"] == [64, 64, 256]
+    assert line["sample_is_whole_single_gpu_lattice"] is True and line["steps"] == 3 and line["warmup"] == 1
+    assert "whole single-GPU lattice" in line["cpu_baseline"]["sample"]
 
 
 def test_traffic_file_is_tied_to_the_kernel_sources():
