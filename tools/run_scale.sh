@@ -1,6 +1,6 @@
 #!/bin/bash
-# usage: tools/run_scale.sh <tag> <ngpus>   -- weak (cfg5w, with e2e) and strong (cfg4, cfg5s) scaling lines on one box
-tag=$1; n=$2
+# usage: tools/run_scale.sh <tag> <ngpus> [what...]  -- weak (cfg5w, with e2e) and strong (cfg4, cfg5s) scaling lines on one box
+tag=$1; n=$2; shift 2; what=${*:-"cfg5w cfg5s cfg4 cfg5s_aa"}
 mkdir -p gpurun_out
 run() { # name, extra args...
   name=$1; shift
@@ -16,7 +16,12 @@ except Exception as ex:
     print('${name} N=$n FAILED', ex); print(open('gpurun_out/${name}_n${n}_$tag.err').read()[-1200:])
 PY
 }
-run cfg5w
-run cfg5s --workload cfg5s --no-e2e
-run cfg4 --workload cfg4 --no-e2e
-run cfg5s_aa --workload cfg5s --no-e2e --in-place
+for w in $what; do
+  case $w in
+    cfg5w) run cfg5w ;;
+    cfg5w_aa) run cfg5w_aa --no-e2e --in-place ;;
+    cfg5s) run cfg5s --workload cfg5s --no-e2e ;;
+    cfg4) run cfg4 --workload cfg4 --no-e2e ;;
+    cfg5s_aa) run cfg5s_aa --workload cfg5s --no-e2e --in-place ;;
+  esac
+done
