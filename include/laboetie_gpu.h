@@ -88,8 +88,13 @@ int lbg_create_slab(lbg_handle* h, int lx, int ly, int lz_global, int k0, int nz
 int lbg_create_geometry(lbg_handle* h, int label, int lx, int ly, int lz_global, int k0, int nzl, int device);
 int lbg_get_nature(lbg_handle h, int8_t* nature);
 int lbg_destroy(lbg_handle h);
-/* NCCL communicator for the slab ring.  Rank 0 obtains the id, the host
- * distributes it (torch.distributed / MPI / a file), every rank calls comm_init. */
+/* Joins the slabs of one node into a ring.  Rank 0 obtains the 128-byte id (an NCCL unique id), the host
+ * distributes it (torch.distributed / MPI / a file), every rank calls comm_init (collective).  The NCCL
+ * communicator only bootstraps the exchange of CUDA IPC handles (a process keeps it and reuses it for later
+ * handles of the same rank): per step the halo planes are pushed by the copy engines over NVLink into small
+ * receive buffers the ring neighbours map, and the scalars (l2err, negative flag, vacf, counts) are all-reduced
+ * through the peers' mailboxes; LBG_HALO=nccl selects ncclSend/ncclRecv + ncclAllReduce instead.
+ * All stepping / set-up calls on slab handles are collective; the read-back calls are local. */
 int lbg_comm_unique_id(void* id_out /* LBG_UNIQUE_ID_BYTES */);
 int lbg_comm_init(lbg_handle h, int nranks, int rank, const void* id);
 
