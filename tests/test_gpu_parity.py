@@ -212,6 +212,40 @@ def test_equilibration_exit_steps_match_reference_semantics():
         assert np.array_equal(sim.lb_populations(), ref["n"])
 
 
+@pytest.mark.parametrize("in_place", [False, True], ids=["two-lattice", "in-place"])
+def test_porous_equilibration_to_convergence_and_tracers(in_place):
+    """A whole run of the reference's two phases on a porous lattice (config-5 geometry, 30 720 nodes): about 1000
+    LB steps through both convergence events of the state machine (force switched on at the first one), then 300
+    propagate steps with adsorption.  Exit steps, the complete l2err history, the final populations and moments,
+    P and Pads bit for bit; the vacf rows to summation order."""
+    lb = _gpu()
+    from laboetie_b200 import driver, synthetic as S
+    nat = S.porous_spheres(48, 40, 16, radius=5)
+    f = [1e-5, 0.0, 2e-5]
+    ref = O.equilibration(nat, f, tau=1.0, target_error=1e-9)
+    assert ref["rc"] == 0 and ref["t_exit"] > 500 and ref["t_fext"] == 4
+    itf = O.detect_interfacial(nat)
+    mp = O.MPState(nat, itf, ref["rho"], ref["jx"], ref["jy"], ref["jz"], f, 0.01, 0.1, 0.01)
+    ref_v = np.array([mp.propagate()[1] for _ in range(300)])
+    with lb.LaboetieGPU(nat) as sim:
+        if in_place:
+            sim.lb_set_in_place(True)
+        r = driver.equilibration(sim, f, tau=1.0, target_error=1e-9, chunk=233)
+        assert (r["rc"], r["t_exit"], r["t_fext"]) == (0, ref["t_exit"], ref["t_fext"])
+        assert np.array_equal(r["l2err"], ref["l2err"])
+        rho, jx, jy, jz = sim.lb_moments()
+        assert np.array_equal(rho, ref["rho"]) and np.array_equal(jx, ref["jx"])
+        assert np.array_equal(jy, ref["jy"]) and np.array_equal(jz, ref["jz"])
+        assert np.array_equal(sim.lb_populations(), ref["n"])
+        d = driver.drop_tracers(sim, f, 0.01, 0.1, 0.01, max_steps=300, chunk=128)
+        assert d["steps"] == 300 and not d["converged"]
+        tol = sum_rtol(18 * nat.size)
+        assert rel_err(d["vacf"][0], mp.vacf0) <= tol
+        assert (np.abs(d["vacf"][1:] - ref_v) <= tol * np.abs(mp.vacf0).max()).all()
+        P, A = sim.mp_download()
+        assert np.array_equal(P, mp.P[0]) and np.array_equal(A, mp.Pads[0])
+
+
 def test_tuto_config1_flow_and_tracers():
     """BASELINE config 1: tuto 1x50x50 one-disk geometry, flow equilibration then moment propagation."""
     lb = _gpu()
