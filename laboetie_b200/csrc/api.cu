@@ -1270,6 +1270,9 @@ int lbg_destroy(lbg_handle h) {
   if (!h) return LBG_OK;
   cudaSetDevice(h->device);
   h->transfers_pending = false;
+  // an exchange whose planes have not been consumed yet (e.g. lbg_mp_init directly followed by lbg_destroy): the
+  // neighbours' pushes into my receive buffer must have landed before it is freed (bounded wait, errors ignored)
+  if (h->p2p && (h->unpack.on || h->xwait)) wait_halo(h);
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->st_comm) cudaStreamSynchronize(h->st_comm);
   if (h->st_ar) cudaStreamSynchronize(h->st_ar);

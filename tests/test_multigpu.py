@@ -179,3 +179,26 @@ def test_dead_neighbour_is_an_error_not_a_hang(monkeypatch):
     res = _run_ranks(2, rank_fn)
     kind, status, dt = res[0]
     assert kind == "error" and status == 12 and dt < 30, res[0]
+
+
+def test_destroy_with_an_exchange_in_flight():
+    """lbg_mp_init ends with the first exchange of P; a driver that destroys its handle right away must not free the
+    receive buffer under the neighbour's push (lbg_destroy drains the pending exchange first)."""
+    from laboetie_b200 import api, slab
+    if _ndev() < 2:
+        pytest.skip("needs 2 GPUs")
+    nat = random_nature(12, 7, 10, 0.25, 9)
+    for _ in range(3):
+        uid = api.comm_unique_id()
+
+        def rank_fn(r):
+            sim = slab.make_slab_sim(nat, r, 2, device=r, unique_id=uid)
+            try:
+                sim.lb_init(1.0)
+                sim.lb_step(3, tau=1.0, check_every=1, target_error=-1.0)
+                return sim.mp_init(0.01, 0.1, 0.01, [1e-4, 0, 0])
+            finally:
+                sim.close()
+
+        a, b = _run_ranks(2, rank_fn)
+        assert np.array_equal(a, b)
