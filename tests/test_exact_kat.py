@@ -245,3 +245,79 @@ def test_cuda_mp_matches_exact(Db, ka, kd, nbt, monkeypatch):
         assert done == MP_STEPS
         P, A = sim.mp_download()
     check_mp(nat, ex, v0, vacf, P, A, f"cuda Db={Db} ka={ka} kd={kd} nbt={nbt}")
+
+
+# --------------------------------------------------------------------------- the reference's own fixture geometry
+def _tuto_state():
+    """BASELINE config 1 (tuto geom.in_chromat_1disks-dia10-1x50x50_v1, a reference input fixture): the flow state
+    after 6 oracle steps (force switched on after step 3), taken exactly as the start of one exact step."""
+    import os
+    from tests.util import GOLDEN
+    nat = O.read_geom_in(os.path.join(GOLDEN, "geom.in_chromat_1disks-dia10-1x50x50_v1"), 1, 50, 50)
+    f = [0.0, 1e-5, 0.0]
+    st = O.LBState(nat, 1.0, 1.0)
+    for _ in range(3):
+        st.step()
+    st.set_force_uniform(f)
+    for _ in range(3):
+        st.step()
+    start = dict(n=st.n.copy(), rho=st.rho.copy(), j=[st.jx.copy(), st.jy.copy(), st.jz.copy()],
+                 F=[st.fx.copy(), st.fy.copy(), st.fz.copy()])
+    return nat, f, st, start
+
+
+_TUTO_CACHE = {}
+
+
+def _tuto_exact():
+    if not _TUTO_CACHE:
+        nat, f, st, start = _tuto_state()
+        ex_lb = exact_lb(nat, start["n"], start["rho"], start["j"], start["F"], 1.0)
+        st.step()          # the oracle's own step 7: rho, j of it feed Phase B below (exact inputs = these fp64 values)
+        rho, j = st.rho.copy(), [st.jx.copy(), st.jy.copy(), st.jz.copy()]
+        global MP_STEPS
+        saved, MP_STEPS = MP_STEPS, 2
+        try:
+            ex_mp = exact_mp(nat, rho, j, f, 0.01, 0.1, 0.01)
+        finally:
+            MP_STEPS = saved
+        _TUTO_CACHE.update(nat=nat, f=f, start=start, ex_lb=ex_lb, st=st, rho=rho, j=j, ex_mp=ex_mp)
+    return _TUTO_CACHE
+
+
+def _check_mp2(nat, ex, vacf0, vacf, P, Pads, what):
+    global MP_STEPS
+    saved, MP_STEPS = MP_STEPS, 2
+    try:
+        check_mp(nat, ex, vacf0, vacf, P, Pads, what)
+    finally:
+        MP_STEPS = saved
+
+
+def test_oracle_on_the_tuto_fixture_matches_exact():
+    c = _tuto_exact()
+    nat, st = c["nat"], c["st"]
+    check_lb(nat, st.n, st.rho, [st.jx, st.jy, st.jz], c["ex_lb"], "oracle, tuto fixture")
+    itf = O.detect_interfacial(nat)
+    mp = O.MPState(nat, itf, c["rho"], *c["j"], c["f"], 0.01, 0.1, 0.01)
+    vacf = [mp.propagate()[1] for _ in range(2)]
+    _check_mp2(nat, c["ex_mp"], mp.vacf0, vacf, mp.P[0], mp.Pads[0], "oracle, tuto fixture")
+
+
+@pytest.mark.gpu
+def test_cuda_on_the_tuto_fixture_matches_exact():
+    import laboetie_b200 as lb
+    c = _tuto_exact()
+    nat, s0 = c["nat"], c["start"]
+    with lb.LaboetieGPU(nat) as sim:
+        sim.lb_upload(s0["n"], s0["rho"], *s0["j"])
+        sim.lb_set_force_field(*s0["F"])
+        done, _, _ = sim.lb_step(1, tau=1.0, check_every=1, target_error=-1.0)
+        assert done == 1
+        got_n = sim.lb_populations()
+        got_rho, jx, jy, jz = sim.lb_moments()
+        check_lb(nat, got_n, got_rho, [jx, jy, jz], c["ex_lb"], "cuda, tuto fixture")
+        v0 = sim.mp_init_from_moments(c["rho"], *c["j"], 0.01, 0.1, 0.01, c["f"])
+        done, _, vacf = sim.mp_step(2)
+        P, A = sim.mp_download()
+    _check_mp2(nat, c["ex_mp"], v0, vacf, P, A, "cuda, tuto fixture")
