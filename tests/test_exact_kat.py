@@ -223,7 +223,27 @@ def test_cuda_lb_step_matches_exact(tau, in_place):
         assert done == 1
         got_n = sim.lb_populations()
         got_rho, jx, jy, jz = sim.lb_moments()
+        profs = [sim.lb_profiles(a) for a in range(3)]
+        flux = sim.lb_total_flux()
+        probe = sim.lb_probe(1, 2, 0)
     check_lb(nat, got_n, got_rho, [jx, jy, jz], ex, f"cuda tau={tau} in_place={in_place}")
+    # A7: plane sums (equilibration.f90:161-172), total flux (:260) and the probe (:187) against exact sums of the
+    # exact moments
+    en, er, ej = ex
+    lz, ly, lx = nat.shape
+    tol = 64 * EPS * 1.5 * nat.size
+    for axis, n_ax in ((0, lx), (1, ly), (2, lz)):
+        for p in range(n_ax):
+            sel = [r for r in X.nodes(nat.shape) if r[axis] == p and nat[r[2], r[1], r[0]] == 0]
+            for d in range(3):
+                assert abs(float(Fr(float(profs[axis][p, d])) - sum(ej[r][d] for r in sel))) <= tol
+            mean = sum(er[r] for r in sel) / max(len(sel), 1)
+            assert abs(float(Fr(float(profs[axis][p, 3])) - mean)) <= tol
+    fl = [r for r in X.nodes(nat.shape) if nat[r[2], r[1], r[0]] == 0]
+    for d in range(3):
+        assert abs(float(Fr(float(flux[d])) - sum(ej[r][d] for r in fl))) <= tol
+        assert abs(float(Fr(float(probe[d])) - ej[(1, 2, 0)][d])) <= tol
+    assert abs(float(Fr(float(probe[3])) - er[(1, 2, 0)])) <= tol
 
 
 @pytest.mark.gpu
