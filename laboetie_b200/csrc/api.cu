@@ -213,6 +213,7 @@ struct lbg_handle_s {
   int grid_lb = 148, grid_mp = 148;
   int lb_minb = 2;  // register-allocation variant of the LB step kernel (see lb_kernels.cu)
   int lb_pipe = 1;             // software-pipelined step kernel (lb_kernels.cu lb_step_pipe_kernel)
+  int mp_arith = 1;            // Phase-B rank-lookup path: arithmetic neighbour ids on regular nodes (LBG_MP_ARITH=0 disables)
   int mp_tpc = 0;              // Phase-B kernel: consecutive tiles per CTA of a grid that covers the tiles (0: persistent grid)
   int lb_tpc = 0;              // tiles per chunk of the dynamic tile schedule of the Phase-A kernels (Geo::tpc; 0 = static)
   int64_t n_fluid = 0, n_if_fluid = 0;  // own planes
@@ -245,6 +246,7 @@ struct lbg_handle_s {
   double* s = nullptr;
   double* P[2] = {nullptr, nullptr};
   double* A[2] = {nullptr, nullptr};
+  uint32_t* rwords = nullptr; // Phase B, rank-lookup path: "regular" bits per group of 32 fids (mp_kernels.cu)
   uint2* awords = nullptr;    // compact adsorbed storage: per group of 32 fids {interfacial bits, first slot} (lbg_internal.h)
   long long a_stride = 0;     // slots per component of A[.]
   SegTable strips;  // over the planes one propagate launch covers (all own planes, or the interior ones)
@@ -777,6 +779,7 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   // one vacf partial per CTA of a propagate launch: at most one per tile of the slab
   CKB(cudaMalloc(&h->partial, 3 * ((size_t)(h->geo.nfa / BLOCK) + 2 + (size_t)h->grid_mp + 8) * sizeof(double)));
   if (const char* e = std::getenv("LBG_MP_TPC")) h->mp_tpc = std::atoi(e) > 0 ? std::atoi(e) : 0;
+  if (const char* e = std::getenv("LBG_MP_ARITH")) h->mp_arith = std::atoi(e) ? 1 : 0;
   // Variant of the Phase-A step kernel (lb_kernels.cu), measured per workload in profiles/ab_r5a.txt:
   //   large slabs: plain kernel, 3 CTAs per SM (80 registers), tiles handed out two at a time by an atomic
   //                counter (cfg5w: 5.44 ms vs 5.70 ms for the static 2-CTA variant);
@@ -1291,6 +1294,7 @@ int lbg_destroy(lbg_handle h) {
   cudaFree(h->words);
   cudaFree(h->gidx);
   cudaFree(h->awords);
+  cudaFree(h->rwords);
   cudaFree(h->f[0]);
   cudaFree(h->f[1]);
   cudaFree(h->jpp[0]);
@@ -2114,10 +2118,16 @@ static int mp_init_impl(lbg_handle h, double Db, double ka, double kd, const dou
     h->a_stride = ((long long)slots + 31) / 32 * 32;
     if (h->a_stride > g.nfa) return fail(h, LBG_ERR_STATE, "adsorbed storage does not fit");  // cannot happen: slots <= nf + 3 nf / 32... guard anyway
   }
+  if (!h->mp_use_nbt) {   // rank-lookup path: nodes whose neighbour ids follow by arithmetic skip the lookups
+    const size_t ngroups = (size_t)(g.nfa >> 5);
+    if (!h->rwords) CK(cudaMalloc(&h->rwords, ngroups * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(h->rwords, 0, ngroups * sizeof(uint32_t), h->st));
+  }
   MPInitArgs a{};
   a.geo = g;
   a.k = h->k;
   a.mom = h->mom;
+  a.rwords = h->mp_use_nbt ? nullptr : h->rwords;
   a.q = h->q;
   a.nbt01 = h->nbt01;
   a.nbt27 = h->nbt27;
@@ -2234,6 +2244,7 @@ int lbg_mp_step(lbg_handle h, int nsteps, double* vacf, int* steps_done, int* co
       a.Anext = h->A[1 - pc];
       a.awords = h->awords;
       a.a_stride = h->a_stride;
+      a.rwords = (h->mp_use_nbt || h->mp_arith == 0) ? nullptr : h->rwords;
       a.ka = h->ka;
       a.kd = h->kd;
       a.one_minus_kd = 1.0 - h->kd;

@@ -142,6 +142,7 @@ struct MPInitArgs {
   int* err;            // set if the remaining fraction < eps somewhere
   uint32_t* nbt01;     // neighbour table words 0,1 (stride nfa), see NBT_* below
   uint32_t* nbt27;     // words 2..4 (stride nfa)
+  uint32_t* rwords;    // per group of 32 fids: bit i = node 32 k + i is "regular" (see mp_init_kernel); may be NULL
 };
 
 // Phase-B neighbour table: the flow AND the geometry are frozen, so the fluid ids of a node's
@@ -199,6 +200,7 @@ struct MPArgs {
   Ctrl* ctrl;
   const uint32_t* nbt01;  // neighbour table (see NBT_*), words 0,1 and 2..4
   const uint32_t* nbt27;
+  const uint32_t* rwords; // rank-lookup path: "regular" bits per group of 32 fids (neighbour ids by arithmetic); may be NULL
   const uint2* awords;    // compact adsorbed storage (see above); Anow / Anext: 3 components of stride a_stride
   long long a_stride;
   int use_nbt;            // 0: resolve neighbours through the rank structure (narrow lattices: every warp has seam nodes)

@@ -125,12 +125,19 @@ __global__ void __launch_bounds__(BLOCK) mp_init_kernel(const __grid_constant__ 
     uint32_t nbw[8];
     // slow: on the periodic x seam, or a derived index (c - 1, c + 1, fid +- 1) would leave [0, nfa)
     bool slow = (nb.oxm != -1) || (nb.oxp != 1) || fid < 1 || fid + 1 >= nfa;
+    // "regular": every fluid neighbour's id is this node's id plus the neighbour's DENSE offset (all nodes in
+    // between are fluid -- whole rows and planes of an open geometry), and a solid neighbour's fid + offset stays
+    // inside the arrays.  Such a node needs neither rank lookups nor the table in the propagate kernel.
+    bool regular = true;
     static_for<1, NV>([&](auto Lc) {
       constexpr int L = decltype(Lc)::value;
       constexpr int LI = inv(L);
       double q = 0.0;
       int fp;
-      const bool fluid_nb = lookup(geo, g + offset_plus<L>(nb), fp);
+      const int off = offset_plus<L>(nb);
+      const bool fluid_nb = lookup(geo, g + off, fp);
+      const long long guess = (long long)fid + off;
+      regular = regular && (fluid_nb ? (long long)fp == guess : (guess >= 0 && guess < nfa));
       if constexpr (cx(L) == 0) {  // centre node of a neighbouring row
         constexpr int R = nbt_row(cy(L), cz(L));
         nbw[R] = (uint32_t)fp | (fluid_nb ? NBT_CENTRE_FLUID : 0u);
@@ -184,6 +191,7 @@ __global__ void __launch_bounds__(BLOCK) mp_init_kernel(const __grid_constant__ 
       pk[0] = NBT_FLAG;
       pk[2] = (uint32_t)g;
     }
+    if (a.rwords && regular) atomicOr(a.rwords + (fid >> 5), 1u << ((uint32_t)fid & 31u));
     a.nbt01[fid] = pk[0];
     a.nbt01[nfa + fid] = pk[1];
     for (int r = 2; r < 5; ++r) a.nbt27[(long long)(r - 2) * nfa + fid] = pk[r];
@@ -271,6 +279,7 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
       for (int r = 2; r < NW; ++r) w_next[r] = ld_stream(a.nbt27 + (long long)(r - 2) * nfa + f);
     } else {
       w_next[0] = __ldg(geo.gidx + f);
+      w_next[1] = a.rwords ? __ldg(a.rwords + (f >> 5)) : 0u;
     }
   };
   if (f_next >= 0) load_words(f_next);
@@ -357,7 +366,18 @@ __global__ void __launch_bounds__(BLOCK, LBG_MP_MINB) mp_step_kernel(const __gri
         });
       }
     } else {
-      resolve_by_lookup((int)(w[0] & GIDX_MASK));
+      const int g = (int)(w[0] & GIDX_MASK);
+      if ((w[1] >> ((uint32_t)fid & 31u)) & 1u) {
+        // regular node (mp_init): neighbour ids by arithmetic, no lookups -- on open geometries (slit, bulk,
+        // wide channels) that is every warp except those next to a wall plane
+        const Nb nb = neighbours(geo, g);
+        static_for<1, NV>([&](auto Lc) {
+          constexpr int L = decltype(Lc)::value;
+          gp[L] = fid + offset_plus<L>(nb);
+        });
+      } else {
+        resolve_by_lookup(g);
+      }
     }
     double q[NV - 1];
     static_for<1, NV>([&](auto Lc) {

@@ -106,3 +106,41 @@ def test_decoded_neighbours_equal_lookups(shape, p, seed):
 def test_reference_geometries():
     for nat in (O.geometry(1, 8, 8, 16), O.geometry(2, 11, 11, 4), O.geometry(3, 12, 12, 12)):
         assert build_and_check(nat) > 0
+
+
+def regular_nodes(nat):
+    """numpy statement of the "regular" bit mp_init_kernel records on the rank-lookup path: every fluid neighbour's
+    fluid id equals the node's own id plus the neighbour's dense offset; a solid neighbour's id + offset is in range."""
+    lz, ly, lx = nat.shape
+    fluid = (nat == 0)
+    flat = fluid.ravel()
+    rank = np.concatenate([[0], np.cumsum(flat)])[:-1]
+    nf = int(flat.sum())
+    nfa = max(32, (nf + 31) // 32 * 32)
+    z, y, x = np.meshgrid(np.arange(lz), np.arange(ly), np.arange(lx), indexing="ij")
+    dense = lambda zz, yy, xx: ((zz % lz) * ly + (yy % ly)) * lx + (xx % lx)   # noqa: E731
+    own = dense(z, y, x)
+    fid = rank[own].astype(np.int64)
+    reg = fluid.copy()
+    for l in range(1, 19):
+        cx, cy, cz = C[l]
+        g = dense(z + cz, y + cy, x + cx)
+        guess = fid + (g - own)                       # own id + dense offset (periodic wraps included)
+        nb_fluid = flat[g]
+        reg &= np.where(nb_fluid, rank[g] == guess, (guess >= 0) & (guess < nfa))
+    return reg, fluid
+
+
+def test_regular_nodes_of_open_and_porous_geometries():
+    """A slit is regular everywhere except in the planes whose solid neighbours would index outside the arrays; a
+    random porous lattice has hardly any regular node.  (Exactness of the rule itself is what the GPU parity tests of the
+    rank-lookup path check: a regular node's arithmetic ids must reproduce the oracle's P bit for bit.)"""
+    nat = O.geometry(1, 16, 12, 20)                  # slit: planes z = 0 and z = lz-1 solid
+    reg, fluid = regular_nodes(nat)
+    assert not reg[~fluid].any()
+    assert reg[2:-2].all()                           # interior planes: all regular
+    assert reg[fluid].mean() > 0.85
+    bulk = O.geometry(-1, 9, 7, 5)                   # all fluid, periodic: every node regular
+    assert regular_nodes(bulk)[0].all()
+    reg, fluid = regular_nodes(random_nature(24, 12, 9, 0.3, 11))
+    assert reg[fluid].mean() < 0.05
