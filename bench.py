@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--check-every", type=int, default=1, help="1 = reference semantics (l2err every step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-reps", type=int, default=2, help="complete end-to-end passes; the faster one is reported")
+    ap.add_argument("--e2e-reps", type=int, default=3, help="complete end-to-end passes; the faster one is reported")
     ap.add_argument("--cpu-seconds", type=float, default=None,
                     help="seconds of CPU stepping the sample is sized for (default: 20 for cpu_baseline, 150 for --impl reference)")
     ap.add_argument("--cpu-lattice", default="sample", choices=["sample", "full"],
@@ -443,7 +443,7 @@ def run_ours(args):
         # 370 ms for the same lbg_create, profiles/create_timing_r5n.txt)
         with lb.LaboetieGPU(np.zeros((4, 8, 32), np.int8), device=local):
             pass
-        # Two repetitions, the faster one is reported (both times are in `seconds_all`): one CUDA call of the set-up
+        # Three repetitions, the fastest one is reported (both times are in `seconds_all`): one CUDA call of the set-up
         # occasionally stalls for 0.3-0.4 s on some boxes of the pool (lbg_create 25-50 ms vs 370-430 ms for identical
         # work, profiles/create_timing_r5n.txt), which says nothing about the path measured.
         best = None

@@ -796,6 +796,10 @@ int create_common(lbg_handle* out, int lx, int ly, int lz_global, int k0, int nz
   h->geo.tpc = h->lb_tpc;
   h->grid_lb = occupancy_grid_lb(h->sm_count, h->lb_minb);
   h->grid_aa = occupancy_grid_aa(h->sm_count);
+  // the small per-32-fid index arrays of Phase B (12 bytes per 32 nodes): allocated here so that lbg_mp_init, which
+  // may run beside a queued multi-GB read-back, allocates nothing
+  CKB(cudaMalloc(&h->awords, (size_t)(h->geo.nfa >> 5) * sizeof(uint2)));
+  CKB(cudaMalloc(&h->rwords, (size_t)(h->geo.nfa >> 5) * sizeof(uint32_t)));
   tm.lap("field allocations");
 #undef CKB
   *out = h;
@@ -2047,6 +2051,7 @@ static int mp_init_impl(lbg_handle h, double Db, double ka, double kd, const dou
   if (Db <= eps) return fail(h, LBG_ERR_TRACER_DB, lbg_status_string(LBG_ERR_TRACER_DB));       // drop_tracers.f90:89
   if (ka < -eps || kd < -eps) return fail(h, LBG_ERR_TRACER_KA_KD, lbg_status_string(LBG_ERR_TRACER_KA_KD));
   CK(cudaSetDevice(h->device));
+  PhaseTimer tm("lbg_mp_init");
   if (host_mom) {
     RET(wait_halo(h));
     CK(cudaMemsetAsync(h->mom, 0, 4 * (size_t)h->geo.nfa * sizeof(double), h->st));
@@ -2107,7 +2112,7 @@ static int mp_init_impl(lbg_handle h, double Db, double ka, double kd, const dou
   h->a_stride = 0;
   if (h->ads) {
     const long long ngroups = g.nfa >> 5;
-    if (!h->awords) CK(cudaMalloc(&h->awords, (size_t)ngroups * sizeof(uint2)));
+    if (!h->awords) CK(cudaMalloc(&h->awords, (size_t)ngroups * sizeof(uint2)));   // normally done in lbg_create*
     h->launches += launch_build_awords(g, own_begin(h), own_end(h), h->awords, h->st);
     CK(cudaMemsetAsync(h->counts, 0, sizeof(unsigned long long), h->st));
     h->launches += launch_scan_ranks(h->awords, ngroups, h->counts, h->st);
@@ -2115,6 +2120,7 @@ static int mp_init_impl(lbg_handle h, double Db, double ka, double kd, const dou
     RET(read_small_async(h, 0, h->counts, sizeof(slots)));
     CK(cudaStreamSynchronize(h->st));
     std::memcpy(&slots, h->h_small, sizeof(slots));
+    tm.lap("moments + awords (first sync)");
     h->a_stride = ((long long)slots + 31) / 32 * 32;
     if (h->a_stride > g.nfa) return fail(h, LBG_ERR_STATE, "adsorbed storage does not fit");  // cannot happen: slots <= nf + 3 nf / 32... guard anyway
   }
@@ -2153,6 +2159,7 @@ static int mp_init_impl(lbg_handle h, double Db, double ka, double kd, const dou
   CK(cudaGetLastError());
   std::memcpy(part.data(), h->h_small, part.size() * sizeof(double));
   std::memcpy(&bad, h->h_small + SMALL_CAP - 64, sizeof(int));
+  tm.lap("init kernel + partials (second sync)");
   double v0[3] = {0, 0, 0};
   for (int b = 0; b < grid; ++b)
     for (int d = 0; d < 3; ++d) v0[d] += part[(size_t)b * 3 + d];
