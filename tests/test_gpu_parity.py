@@ -246,8 +246,9 @@ def test_porous_equilibration_to_convergence_and_tracers(in_place):
         assert np.array_equal(P, mp.P[0]) and np.array_equal(A, mp.Pads[0])
 
 
-def test_tuto_config1_flow_and_tracers():
-    """BASELINE config 1: tuto 1x50x50 one-disk geometry, flow equilibration then moment propagation."""
+def test_tuto_config1_against_oracle_derived_golden():
+    """BASELINE config 1: tuto 1x50x50 one-disk geometry, flow equilibration then moment propagation, against
+    tests/golden/tuto_cfg1_oracle.npz -- ORACLE output (tests/golden/make_golden.py), a regression pin, not a reference pin."""
     lb = _gpu()
     from laboetie_b200 import driver
     import os
